@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the line-of-sight integration hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nside 2048]
+
+Workload (BASELINE.json configs[2]): Planck18 model at 857 GHz, full-sky HEALPix nside=2048 map
+(50 331 648 lines of sight x 4 components x 50 Gauss-Legendre nodes = 1.0066e10 evaluations per
+step), synthetic pointings = HEALPix RING pixel centres taken as ecliptic unit vectors, single
+obstime, observer = Earth.  One "step" = one full map.  With N GPUs the map is sharded
+contiguously (np.array_split rule), each rank integrates its slice and an NCCL all-gather
+assembles the map on every rank ("strong" scaling: total work fixed).
+
+Prints ONE JSON line (rank 0).  `value` = evaluations/s with inputs resident in HBM; `e2e` = the
+same through the C-ABI call with pinned HOST buffers (H2D + kernel + D2H inside the timed region).
+`--impl reference` times the CPU port of the reference's path (oracle/, the reference is pure
+Python and cannot travel to the GPU box) with the reference's own fork-pool parallel driver.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LOS evaluations/s (pixel x component x quadrature node)"
+UNIT = "evals/s"
+MODEL_NAME, X_GHZ, DEG = "planck18", 857.0, 50
+FLOPS_PER_UNIT = 60.25  # canonical algorithmic flops, Planck-type 4-comp mean
+SFU_PER_UNIT = 7.0
+EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])  # 2022-01-14, SURVEY.md 8(d)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nside", type=int, default=2048)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(nside, n_gpus, precision):
+    return {"workload": f"{MODEL_NAME} {X_GHZ:g} GHz, HEALPix nside={nside} full-sky map "
+                        f"({12 * nside * nside} lines of sight x 4 comps x {DEG} nodes), single obstime, "
+                        "observer=earth (BASELINE configs[2])",
+            "precision_mode": precision, "nside": nside, "n_los": 12 * nside * nside, "ncomps": 4,
+            "gauss_quad_degree": DEG, "sharding": f"contiguous x{n_gpus} + allgather",
+            "l2": "inputs (24 B/line of sight, >= 1.2 GB per step at 1 GPU) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax, power = [], set(), None, []
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power) if power else None)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path driven like zodipy/model.py:182-198."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zodi_oracle as oracle
+    import zodipy_b200 as zp
+    from zodipy_b200 import healpix
+
+    cores = os.cpu_count() or 1
+    model = zp.Model(zp.Quantity(X_GHZ, "GHz"), name=MODEL_NAME, gauss_quad_degree=DEG)
+    spec = model.spec
+    npix = healpix.nside2npix(args.nside)
+    rng = np.random.default_rng(0)
+    # calibrate one core, then size a sample for ~3 s per step on all cores
+    cal = healpix.pix2vec_ring(args.nside, np.sort(rng.choice(npix, 4000, replace=False)))
+    t0 = time.perf_counter()
+    oracle.evaluate(spec, cal, EARTH, EARTH)
+    per_pix_core = (time.perf_counter() - t0) / 4000
+    n_sample = int(min(npix, max(cores * 2000, 3.0 * cores / per_pix_core)))
+    u = healpix.pix2vec_ring(args.nside, np.sort(rng.choice(npix, n_sample, replace=False)))
+    units = n_sample * 4 * DEG
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle.evaluate_parallel(spec, u, EARTH, EARTH, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.evaluate_parallel(spec, u, EARTH, EARTH, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = units / dt
+    sample = (f"{n_sample} randomly chosen pixels of the nside={args.nside} map per step "
+              f"({units:.3g} evaluations), fork Pool({cores}) like zodipy/model.py:182-198")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (npix / n_sample),
+        "ms_per_sample_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.nside, args.gpus, "fp64 (NumPy)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_baseline(spec, nside, budget_s=12.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zodi_oracle as oracle
+    from zodipy_b200 import healpix
+
+    cores = os.cpu_count() or 1
+    npix = healpix.nside2npix(nside)
+    rng = np.random.default_rng(0)
+    cal = healpix.pix2vec_ring(nside, np.sort(rng.choice(npix, 4000, replace=False)))
+    t0 = time.perf_counter()
+    oracle.evaluate(spec, cal, EARTH, EARTH)
+    per_pix_core = (time.perf_counter() - t0) / 4000
+    n_sample = int(min(npix, max(cores * 2000, budget_s * cores / per_pix_core)))
+    u = healpix.pix2vec_ring(nside, np.sort(rng.choice(npix, n_sample, replace=False)))
+    t0 = time.perf_counter()
+    oracle.evaluate_parallel(spec, u, EARTH, EARTH, cores)
+    dt = time.perf_counter() - t0
+    units = n_sample * len(spec["comps"]) * len(spec["points"])
+    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_sample} random pixels of the nside={nside} map ({units:.3g} evaluations, "
+                      f"{dt:.1f} s) with the oracle port under fork Pool({cores}) (zodipy/model.py:182-198)",
+            "single_core_evals_per_s": 4 * DEG / per_pix_core}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import zodipy_b200 as zp
+    from zodipy_b200 import engine, healpix, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    precision = args.precision
+    out_dtype = np.float32 if precision == "fp32" else np.float64
+    model = zp.Model(zp.Quantity(X_GHZ, "GHz"), name=MODEL_NAME, gauss_quad_degree=DEG,
+                     precision=precision, device=local_rank)
+    dm = model.device_model
+    npix = healpix.nside2npix(args.nside)
+    ncomps = model.ncomps
+    lo, hi = sharding.split_bounds(npix, world)[rank]
+    n_local = hi - lo
+    units_total = npix * ncomps * DEG
+
+    # ---- inputs: pinned host copy (for e2e) and HBM-resident copy (for value) ----
+    u_host = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
+    healpix.full_sky_vectors(args.nside, lo, hi, out=u_host.numpy())
+    u_dev = u_host.to(dev, non_blocking=True)
+    obs_dev = torch.as_tensor(EARTH, device=dev)
+    flags = dm.outside_flags(EARTH)
+    tdtype = torch.float32 if precision == "fp32" else torch.float64
+    out_local = torch.empty(n_local, dtype=tdtype, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
+                    outside_flags=flags)
+        if world > 1:
+            return sharding.allgather_map(out_local, npix)
+        return out_local
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        full = step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = engine.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                for _ in range(args.steps)]
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        k_events[i][0].record()
+        dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
+                    outside_flags=flags)
+        k_events[i][1].record()
+        if world > 1:
+            full = sharding.allgather_map(out_local, npix)
+    e1.record()
+    barrier()
+    launches = engine.kernel_launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = float(t[0]), float(t[1])
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = elapsed_ms / args.steps
+    value = units_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API with pinned HOST buffers, H2D + kernel + D2H in the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        out_host = torch.empty(n_local, dtype=tdtype).pin_memory()
+        u_np, out_np = u_host.numpy(), out_host.numpy()
+        n_e2e = max(3, min(args.steps, 5))
+        for _ in range(2):
+            model.evaluate_xyz(u_np, EARTH, EARTH, out=out_np, out_dtype=out_dtype, outside_flags=flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            model.evaluate_xyz(u_np, EARTH, EARTH, out=out_np, out_dtype=out_dtype, outside_flags=flags)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {"value": units_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "h2d_bytes_per_step": int(3 * 8 * npix + 6 * 8 * world),
+               "d2h_bytes_per_step": int(npix * out_host.element_size()),
+               "api": "Model.evaluate_xyz(numpy pinned host arrays) -> zodi_evaluate(ZODI_MEM_HOST)"}
+        # sanity: e2e result equals the device-resident result
+        assert np.array_equal(out_np, out_local.cpu().numpy()), "host-path result differs from device path"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: pipe peaks measured live on this GPU ----
+    peak_fp32 = engine.peak_probe("fp32", local_rank)
+    peak_fp64 = engine.peak_probe("fp64", local_rank)
+    peak_mufu = engine.peak_probe("mufu", local_rank)
+    per_gpu_units = n_local * ncomps * DEG
+    kernel_units_per_s = per_gpu_units / (kernel_ms * 1e-3)
+    peak = peak_fp32 if precision == "fp32" else peak_fp64
+    achieved = kernel_units_per_s * FLOPS_PER_UNIT
+    roofline = {
+        "bound": precision, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": None,
+        "kernel": "zodi_los_generic_kernel", "kernel_ms": kernel_ms,
+        "flops_per_unit_canonical": FLOPS_PER_UNIT, "sfu_per_unit_canonical": SFU_PER_UNIT,
+        "sfu_frac": kernel_units_per_s * SFU_PER_UNIT / peak_mufu,
+        "peaks_measured": {"fp32_tflops": peak_fp32 / 1e12, "fp64_tflops": peak_fp64 / 1e12,
+                           "mufu_tops": peak_mufu / 1e12,
+                           "how": "zodi_peak_probe: FFMA / DFMA / MUFU.EX2 microbenchmarks, best of 5, "
+                                  "same process, same GPU"},
+        "algorithmic_hbm_bytes_per_los": 24 + (4 if precision == "fp32" else 8),
+        "note": "compute-pipe bound (HBM traffic is 28-32 B per 200 evaluations); `peak` is the measured "
+                "pipe peak of the precision mode, not HBM/tensor",
+    }
+
+    # ---- accuracy of the timed configuration vs the oracle on a sample ----
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zodi_oracle as oracle
+
+    sel = np.sort(np.random.default_rng(1).choice(n_local, 2000, replace=False))
+    ref = oracle.evaluate(model.spec, u_host.numpy()[:, sel], EARTH, EARTH).sum(axis=0)
+    got = out_local.cpu().numpy()[sel]
+    max_rel = float(np.max(np.abs(got - ref) / np.abs(ref)))
+
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(model.spec, args.nside)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f64",
+        "data": "synthetic", "config": workload_config(args.nside, world, precision),
+        "pixels_per_s": npix / (ms_per_step * 1e-3),
+        "max_rel_err_vs_oracle": max_rel, "tolerance": 1e-5 if precision == "fp32" else 1e-10,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+/*
+ * zodi_b200.h - C ABI of the B200-native line-of-sight brightness integrator.
+ *
+ * This is the drop-in boundary for ZodiPy's array-only hot path.  The reference
+ * (Cosmoglobe/zodipy v1.1.3, pure Python/NumPy) has no FFI; the seam this ABI replaces is the
+ * array tail of `Model._evaluate`, /root/reference/zodipy/model.py:253-279, i.e.
+ *
+ *   get_line_of_sight_range()          zodipy/line_of_sight.py:88-105   (+ :64-85)
+ *   integrate_leggauss()               zodipy/line_of_sight.py:55-61
+ *   kelsall_brightness_at_step()       zodipy/brightness.py:21-56
+ *   rrm_brightness_at_step()           zodipy/brightness.py:59-83
+ *   get_dust_grain_temperature()       zodipy/blackbody.py:16-30
+ *   np.interp(T, *bp_interpolation_table)   zodipy/brightness.py:48,81
+ *   get_scattering_angle()/get_phase_function()   zodipy/scattering.py:11-59
+ *   DENSITY_FUNCS[...]                 zodipy/number_density.py:47-420
+ *
+ * Everything is plain C: pointers, sizes, POD structs.  No torch / C++ types cross the ABI.
+ * All functions return 0 (ZODI_OK) on success or a negative zodi_status; the message of the
+ * last failure on the calling thread is available from zodi_last_error().  Nothing throws.
+ *
+ * The library is CUDA-only (sm_100a).  There is no CPU fallback: if no CUDA device is usable
+ * every compute entry point fails with ZODI_ERR_CUDA.
+ */
+#ifndef ZODI_B200_H
+#define ZODI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZODI_ABI_VERSION 1
+#define ZODI_MAX_COMPS 16   /* reference models have 4, 6 or 8 components */
+#define ZODI_MAX_NODES 1024 /* gauss_quad_degree upper bound (reference default: 50) */
+#define ZODI_MAX_TEMPS 1024 /* blackbody table knots (reference: 100, zodipy/blackbody.py:11) */
+#define ZODI_N_SHAPE 8
+
+typedef enum {
+    ZODI_OK = 0,
+    ZODI_ERR_INVALID = -1, /* bad argument / descriptor */
+    ZODI_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+    ZODI_ERR_NOMEM = -3,
+    ZODI_ERR_UNSUPPORTED = -4
+} zodi_status;
+
+/* Component density types = keys of DENSITY_FUNCS, zodipy/number_density.py:408-420.
+ * shape[] holds the RAW reference parameters (dataclass fields, zodipy/component.py:47-204) in
+ * the order given below; angles already in the *_rad form the reference's density functions
+ * consume (component.py:85-89,130-136).  The library derives its own device-side constants. */
+typedef enum {
+    ZODI_CLOUD = 0,        /* n_0, alpha, beta, gamma, mu                         :47-73   */
+    ZODI_BAND = 1,         /* n_0, delta_zeta_rad, v, p, delta_r                  :76-110  */
+    ZODI_RING = 2,         /* n_0, R, sigma_r, sigma_z                            :113-139 */
+    ZODI_FEATURE = 3,      /* n_0, R, sigma_r, sigma_z, theta_rad, sigma_theta_rad :142-181 */
+    ZODI_FAN = 4,          /* Q, P, gamma, Z_0, R_outer                           :184-218 */
+    ZODI_COMET = 5,        /* gamma, Z_0, P, amp, R_inner, R_outer                :221-256 */
+    ZODI_INTERSTELLAR = 6, /* amp                                                 :259-264 */
+    ZODI_NARROW_BAND = 7,  /* beta_nb, G, gamma, A, R_inner, R_outer              :267-304 */
+    ZODI_BROAD_BAND = 8,   /* beta_bb, sigma_bb, gamma, A, R_inner, R_outer       :307-342 */
+    ZODI_RING_RRM = 9,     /* n_0, R, sigma_r, sigma_z, A                         :345-370 */
+    ZODI_FEATURE_RRM = 10, /* n_0, R, sigma_r, sigma_z, theta_rad, sigma_theta_rad, A :373-404 */
+    ZODI_N_COMP_TYPES = 11
+} zodi_comp_type;
+
+typedef enum { ZODI_KELSALL = 0, ZODI_RRM = 1 } zodi_model_kind; /* zodiacal_light_model.py:72-102 */
+typedef enum { ZODI_FP64 = 0, ZODI_FP32 = 1 } zodi_precision;
+typedef enum { ZODI_OUT_F64 = 0, ZODI_OUT_F32 = 1 } zodi_out_dtype;
+typedef enum { ZODI_MEM_HOST = 0, ZODI_MEM_DEVICE = 1 } zodi_memory;
+
+/* One dust component: geometry (zodipy/component.py:27-44), shape parameters, the two
+ * heliocentric cutoff radii of its line-of-sight range (COMPONENT_CUTOFFS,
+ * zodipy/line_of_sight.py:19-52) and its source-function scalars
+ * (zodipy/unpack_model.py:34-57 Kelsall: emissivity, albedo; :120-126 RRM: T_0, delta). */
+typedef struct {
+    int32_t type; /* zodi_comp_type */
+    int32_t reserved;
+    double x0[3];
+    double sin_Omega, cos_Omega, sin_i, cos_i;
+    double shape[ZODI_N_SHAPE];
+    double cutoff_inner, cutoff_outer;
+    double emissivity, albedo; /* Kelsall kind */
+    double T_0, delta;         /* RRM kind (per component) */
+} zodi_component_desc;
+
+/* Everything `Model.__init__` prepares for the hot path (zodipy/model.py:101-108,281-301). */
+typedef struct {
+    int32_t abi_version; /* must be ZODI_ABI_VERSION */
+    int32_t kind;        /* zodi_model_kind */
+    int32_t n_comps;
+    int32_t n_nodes; /* gauss_quad_degree */
+    int32_t n_temps; /* knots of the blackbody table */
+    int32_t reserved;
+    /* Kelsall shared source parameters (zodipy/unpack_model.py:34-105) */
+    double T_0, delta, C1, C2, C3, solar_irradiance;
+    /* RRM shared source parameter (zodipy/unpack_model.py:128-136) */
+    double calibration;
+    /* bp_interpolation_table rows (zodipy/blackbody.py:44-49): temperatures must be uniformly
+     * spaced and ascending (the reference's are linspace(40, 550, 100)); bnu in MJy/sr. */
+    const double* temps;
+    const double* bnu;
+    /* np.polynomial.legendre.leggauss(n_nodes), zodipy/model.py:103 */
+    const double* nodes;
+    const double* weights;
+    zodi_component_desc comps[ZODI_MAX_COMPS];
+} zodi_model_desc;
+
+typedef struct zodi_model_s* zodi_model_t;
+
+/* Arguments of one evaluation = the arrays at the seam zodipy/model.py:253-279.
+ * Layout is the reference's: structure-of-arrays, row k of a (3, n) array starts at
+ * ptr + k*stride (stride >= n, in elements), so a contiguous shard of a larger (3, N) array can
+ * be passed without copying (np.array_split on the last axis, zodipy/model.py:184-188). */
+typedef struct {
+    int64_t n;          /* number of lines of sight in this call */
+    const double* u;    /* (3, n) ecliptic unit vectors, model.py:249-251 */
+    int64_t u_stride;
+    const double* obs;  /* (3, n_obs) observer position [AU], model.py:232-239 */
+    int64_t n_obs;      /* 1 (instantaneous) or n (time-ordered) */
+    int64_t obs_stride;
+    const double* earth; /* (3, n_earth) Earth position [AU], model.py:213-220,240-241 */
+    int64_t n_earth;     /* 1 or n */
+    int64_t earth_stride;
+    /* (n_comps, 2) bytes, ALWAYS host memory: [c][0] != 0 <=> any observer of the WHOLE job is
+     * outside component c's inner cutoff sphere, [c][1] likewise for the outer one (the global
+     * `.any()` early-out of get_sphere_intersection, line_of_sight.py:72-73).
+     * NULL: the library derives the flags from the observers of THIS call. */
+    const uint8_t* outside_flags;
+    int32_t return_comps; /* 0: out is (n,) sum over components; 1: out is (n_comps, n) */
+    int32_t precision;    /* zodi_precision */
+    int32_t out_dtype;    /* zodi_out_dtype */
+    int32_t memory;       /* zodi_memory: where u/obs/earth/out live */
+    void* out;
+    int64_t out_stride; /* row stride of out in elements when return_comps (>= n) */
+    void* stream;       /* cudaStream_t for ZODI_MEM_DEVICE (NULL = default stream); async.
+                           ZODI_MEM_HOST calls are synchronous and ignore it. */
+} zodi_eval_args;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int zodi_abi_version(void);
+const char* zodi_last_error(void);
+int zodi_device_count(int* count);
+
+/* ---- model handle: device copy of the parameter block on one GPU -------------------------- */
+int zodi_model_create(const zodi_model_desc* desc, int device, zodi_model_t* out);
+int zodi_model_update(zodi_model_t model, const zodi_model_desc* desc); /* Model.update_parameters */
+int zodi_model_destroy(zodi_model_t model);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);
+
+/* Largest heliocentric observer distance sqrt(x^2+y^2+z^2) over (3, n_obs) observers and the
+ * resulting early-out flags; used to form the GLOBAL flags when a job is sharded over GPUs
+ * (max-reduce r_max over ranks, then zodi_flags_from_radius). */
+int zodi_max_observer_radius(zodi_model_t model, const double* obs, int64_t n_obs,
+                             int64_t obs_stride, int32_t memory, void* stream, double* r_max);
+int zodi_flags_from_radius(zodi_model_t model, double r_max, uint8_t* flags /* (n_comps,2) */);
+
+/* ---- measurement support ------------------------------------------------------------------ */
+typedef enum {
+    ZODI_PEAK_FP32_FMA = 0, /* FFMA  : flop/s (2 per FMA)      */
+    ZODI_PEAK_FP64_FMA = 1, /* DFMA  : flop/s (2 per FMA)      */
+    ZODI_PEAK_MUFU_EX2 = 2, /* MUFU.EX2 : op/s                 */
+    ZODI_PEAK_HBM_COPY = 3  /* device copy: bytes/s (read+write) */
+} zodi_peak_kind;
+int zodi_peak_probe(int device, int32_t kind, double* per_second);
+/* Number of kernels this library launched on behalf of the calling process (all threads). */
+int64_t zodi_kernel_launch_count(void);
+/* Device time [ms] of the LAST zodi_evaluate kernel(s) issued with ZODI_MEM_HOST memory
+ * (CUDA events around the kernels only, excluding copies); for reporting. */
+double zodi_last_kernel_ms(zodi_model_t model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZODI_B200_H */

@@ -1,0 +1,77 @@
+"""Shared test helpers: golden fixtures, synthetic inputs, error metrics."""
+from __future__ import annotations
+
+import functools
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# tolerances stated by BASELINE.json north_star
+TOL_FP64 = 1e-10
+TOL_FP32 = 1e-5
+# Per-component comparisons are relative to max(|ref_c|, floor * |ref_total|).
+# fp64: the reference evaluates the band term `1 - exp(-(R/delta_r)**20)` literally
+# (number_density.py:108); for R < ~0.78 AU its own result carries relative rounding noise
+# eps / (R/delta_r)**20 > 1e-10, on components that are < 1e-9 of the total.  A floor of 1e-6 of the
+# total keeps those noise-dominated values from being compared digit for digit.
+COMP_FLOOR_FP64 = 1e-6
+# fp32: components are gated against max(|component|, |total|) (SURVEY.md 8(a) fp32 note).
+COMP_FLOOR_FP32 = 1.0
+
+
+@functools.lru_cache(maxsize=None)
+def golden_cases():
+    with open(os.path.join(GOLDEN_DIR, "cases.json")) as fh:
+        cases = json.load(fh)["cases"]
+    for c in cases:
+        for k in ("table", "points", "weights"):
+            c["spec"][k] = np.asarray(c["spec"][k], dtype=np.float64)
+    return {c["id"]: c for c in cases}
+
+
+@functools.lru_cache(maxsize=None)
+def golden_arrays():
+    return np.load(os.path.join(GOLDEN_DIR, "cases.npz"))
+
+
+def golden_case(case_id):
+    c = golden_cases()[case_id]
+    a = golden_arrays()
+    return c, {k: a[f"{case_id}/{k}"] for k in ("u", "obs", "earth", "emission", "start", "stop")}
+
+
+def case_ids():
+    return list(golden_cases())
+
+
+def max_rel_total(em, ref):
+    """Max relative error of the component-summed emission."""
+    t, tr = em.sum(axis=0), ref.sum(axis=0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.abs(t - tr) / np.abs(tr)
+    assert not np.any(np.isnan(t) != np.isnan(tr)), "NaN pattern differs"
+    return float(np.nanmax(e))
+
+
+def max_rel_comps(em, ref, floor=0.0):
+    """Max per-component error relative to max(|ref_c|, floor * |ref_total|)."""
+    tr = np.abs(ref.sum(axis=0))[None, :]
+    scale = np.maximum(np.abs(ref), floor * tr)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.where(scale > 0, np.abs(em - ref) / scale, np.abs(em - ref))
+    return float(np.nanmax(e))
+
+
+def fibonacci_sphere(n, seed_shift=0.5):
+    """Deterministic quasi-uniform unit vectors (3, n)."""
+    i = np.arange(n) + seed_shift
+    z = 1.0 - 2.0 * i / n
+    phi = np.pi * (1.0 + 5.0**0.5) * i
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    return np.ascontiguousarray(np.array([r * np.cos(phi), r * np.sin(phi), z]))
+
+
+EARTH_20220114 = np.array([[-0.3919640703], [0.9020953332], [0.0]])

@@ -1,0 +1,51 @@
+// zodi_emu.cpp - HOST build of the device routines in zodipy_b200/csrc/zodi_device.cuh.
+//
+// TEST TOOL ONLY (lives under tests/): lets the CPU-only test-suite exercise the exact arithmetic
+// the CUDA kernels run - descriptor -> device-form constants -> integrate_line_of_sight<Real>() -
+// without a GPU, so formula/constant mistakes are caught before GPU time is spent.  It is never
+// built into, loaded by, or reachable from the product library (zodipy_b200/libzodi_b200.so).
+// fp32 MUFU intrinsics are replaced by libm here, so fp32 results are a lower bound on the GPU's
+// rounding error, not a bit-exact emulation.
+#include <cstdint>
+#include <vector>
+
+#include "../../zodipy_b200/csrc/zodi_model_build.hpp"
+
+using namespace zodi;
+
+template <typename Real>
+static void run(const zodi_model_desc* d, const DevModel<Real>& M, const std::vector<Pair<Real>>& tab,
+                const std::vector<Pair<Real>>& nodes, int64_t n, const double* u, const double* obs,
+                int64_t n_obs, const double* earth, int64_t n_earth, const uint8_t* flags,
+                int lanes, double* out /* (n_comps, n) */) {
+    uint32_t mask = 0;
+    for (int c = 0; c < d->n_comps; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+        for (int c = 0; c < d->n_comps; ++c) out[c * n + j] = 0.0;
+        for (int sub = 0; sub < lanes; ++sub)  // emulate the L lanes of a line of sight serially
+            integrate_line_of_sight<Real>(
+                M, tab.data(), nodes.data(), u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo],
+                obs[2 * n_obs + jo], earth[je], earth[n_earth + je], mask, sub, lanes,
+                [&](int ci, Real part) { out[ci * n + j] += (double)part; });
+    }
+}
+
+extern "C" int zodi_emu_evaluate(const zodi_model_desc* d, int precision, int lanes, int64_t n,
+                                 const double* u, const double* obs, int64_t n_obs,
+                                 const double* earth, int64_t n_earth, const uint8_t* flags,
+                                 double* out) {
+    DevModel<double> m64;
+    DevModel<float> m32;
+    build_dev_model(*d, m64);
+    narrow_model(m64, m32);
+    std::vector<Pair<double>> t64, n64;
+    std::vector<Pair<float>> t32, n32;
+    build_pairs(*d, t64, n64, t32, n32);
+    if (precision == ZODI_FP32) run<float>(d, m32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+    else run<double>(d, m64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+    return 0;
+}

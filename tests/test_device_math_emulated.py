@@ -1,0 +1,70 @@
+"""CPU check of the arithmetic the CUDA kernels run.
+
+tests/host_emu/zodi_emu.cpp compiles the SAME header the kernels are built from
+(zodipy_b200/csrc/zodi_device.cuh + zodi_model_build.hpp) for the host, so the descriptor ->
+device-constant derivation and the fused per-line-of-sight routine are compared with the
+reference's outputs without a GPU.  This is a test tool: the product never loads it.
+The real parity gate is tests/test_gpu_parity.py (-m gpu) through the C ABI.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import zodi_oracle as oracle
+from helpers import COMP_FLOOR_FP64, TOL_FP32, TOL_FP64, case_ids, golden_case, max_rel_comps, max_rel_total
+from zodipy_b200.spec import pack_desc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emu", "zodi_emu.cpp")
+LIB = os.path.join(HERE, "host_emu", "libzodi_emu.so")
+DEPS = [SRC] + [os.path.join(HERE, "..", "zodipy_b200", "csrc", f)
+                for f in ("zodi_device.cuh", "zodi_model_build.hpp")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, SRC],
+                       check=True)
+    return C.CDLL(LIB)
+
+
+def run_emu(emu, spec, u, obs, earth, precision, lanes):
+    desc, keep = pack_desc(spec)
+    u, obs, earth = (np.ascontiguousarray(a, dtype=np.float64) for a in (u, obs, earth))
+    flags = oracle.outside_flags(spec, obs)
+    out = np.zeros((len(spec["comps"]), u.shape[1]))
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = emu.zodi_emu_evaluate(C.byref(desc), precision, lanes, C.c_int64(u.shape[1]), ptr(u), ptr(obs),
+                               C.c_int64(obs.shape[1]), ptr(earth), C.c_int64(earth.shape[1]),
+                               ptr(flags), ptr(out))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("case_id", case_ids())
+def test_fp64_arithmetic_matches_reference(emu, case_id):
+    case, a = golden_case(case_id)
+    em = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 0, 1)
+    assert max_rel_total(em, a["emission"]) <= TOL_FP64
+    assert max_rel_comps(em, a["emission"], floor=COMP_FLOOR_FP64) <= TOL_FP64
+
+
+@pytest.mark.parametrize("lanes", [2, 8, 32])
+def test_fp64_lane_split_is_equivalent(emu, lanes):
+    case, a = golden_case("dirbe_25um_rand")
+    em = run_emu(emu, case["spec"], a["u"][:, :200], a["obs"], a["earth"], 0, lanes)
+    assert max_rel_total(em, a["emission"][:, :200]) <= TOL_FP64
+
+
+@pytest.mark.parametrize("case_id", case_ids())
+def test_fp32_arithmetic_within_tolerance(emu, case_id):
+    """fp32 formulation (libm instead of MUFU): total within 1e-5; components within 1e-5 of
+    max(|component|, |total|) (SURVEY 8(a) fp32 note)."""
+    case, a = golden_case(case_id)
+    em = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1)
+    assert max_rel_total(em, a["emission"]) <= TOL_FP32
+    assert max_rel_comps(em, a["emission"], floor=1.0) <= TOL_FP32

@@ -1,0 +1,165 @@
+"""Parity of the CUDA path (through the C ABI) with the reference / oracle.  Needs a GPU."""
+import numpy as np
+import pytest
+
+import zodi_oracle as oracle
+import zodipy_b200 as zp
+from helpers import (COMP_FLOOR_FP32, COMP_FLOOR_FP64, EARTH_20220114, TOL_FP32, TOL_FP64, case_ids,
+                     fibonacci_sphere, golden_case, max_rel_comps, max_rel_total)
+from zodipy_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp64": (TOL_FP64, COMP_FLOOR_FP64), "fp32": (TOL_FP32, COMP_FLOOR_FP32)}
+
+
+def device_model(spec):
+    return engine.DeviceModel(spec, device=0)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("case_id", case_ids())
+def test_golden_host_memory(case_id, precision):
+    """Committed reference outputs, C-ABI call with HOST buffers (H2D + kernel + D2H)."""
+    case, a = golden_case(case_id)
+    dm = device_model(case["spec"])
+    launches = engine.kernel_launch_count()
+    em = dm.evaluate(a["u"], a["obs"], a["earth"], return_comps=True, precision=precision)
+    assert engine.kernel_launch_count() > launches  # the CUDA kernels ran
+    tol, floor = TOL[precision]
+    assert em.shape == a["emission"].shape and em.dtype == np.float64
+    assert max_rel_total(em, a["emission"]) <= tol
+    assert max_rel_comps(em, a["emission"], floor=floor) <= tol
+    total = dm.evaluate(a["u"], a["obs"], a["earth"], return_comps=False, precision=precision)
+    assert total.shape == (a["u"].shape[1],)
+    # summed output = component sum in model order (comps.sum(axis=0), tests/test_evaluate.py:198-212)
+    np.testing.assert_allclose(total, em.sum(axis=0), rtol=1e-6 if precision == "fp32" else 1e-15)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("case_id", ["dirbe_25um_rand", "dirbe_1p25um_tod", "rrm_60um", "planck18_tod",
+                                     "dirbe_25um_tod_straddle"])
+def test_golden_device_memory(case_id, precision):
+    """Same through device-resident torch tensors (async launch on the current stream)."""
+    import torch
+
+    case, a = golden_case(case_id)
+    dm = device_model(case["spec"])
+    dev = torch.device("cuda:0")
+    u, obs, earth = (torch.as_tensor(a[k], device=dev) for k in ("u", "obs", "earth"))
+    em = dm.evaluate(u, obs, earth, return_comps=True, precision=precision)
+    assert em.is_cuda and tuple(em.shape) == a["emission"].shape
+    em = em.cpu().numpy()
+    tol, floor = TOL[precision]
+    assert max_rel_total(em, a["emission"]) <= tol
+    assert max_rel_comps(em, a["emission"], floor=floor) <= tol
+    out32 = dm.evaluate(u, obs, earth, return_comps=False, precision=precision, out_dtype=np.float32)
+    assert out32.dtype == torch.float32
+    np.testing.assert_allclose(out32.cpu().numpy(), a["emission"].sum(axis=0), rtol=2e-6 + tol)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name,x,unit,n", [("dirbe", 25.0, "um", 49152), ("planck18", 857.0, "GHz", 20000),
+                                           ("planck13", 545.0, "GHz", 20000),
+                                           ("rrm-experimental", 25.0, "um", 6000)])
+def test_against_oracle_on_fresh_inputs(name, x, unit, n, precision):
+    """CUDA vs oracle on seeded inputs that are not in the fixtures (BASELINE config 1 is the
+    full nside=64-sized dirbe 25 um case)."""
+    model = zp.Model(zp.Quantity(x, unit), name=name, precision=precision)
+    u = fibonacci_sphere(n)
+    em = model.evaluate_xyz(u, EARTH_20220114, return_comps=True)
+    sel = np.random.default_rng(0).choice(n, size=3000, replace=False)
+    ref = oracle.evaluate(model.spec, u[:, sel], EARTH_20220114, EARTH_20220114)
+    tol, floor = TOL[precision]
+    assert max_rel_total(em[:, sel], ref) <= tol
+    assert max_rel_comps(em[:, sel], ref, floor=floor) <= tol
+
+
+def test_edge_shapes_and_chunking():
+    """Empty, single and ragged sizes; sizes that straddle the lane-count and chunk thresholds."""
+    model = zp.Model(zp.Quantity(25.0, "um"))
+    dm = model.device_model
+    assert dm.evaluate(np.zeros((3, 0)), EARTH_20220114).shape == (0,)
+    assert dm.evaluate(np.zeros((3, 0)), EARTH_20220114, return_comps=True).shape == (6, 0)
+    u_all = fibonacci_sphere(400000)
+    full = dm.evaluate(u_all, EARTH_20220114, return_comps=True)
+    for n in (1, 2, 31, 33, 255, 257, 9472, 9473, 303105):
+        part = dm.evaluate(u_all[:, :n], EARTH_20220114, return_comps=True)
+        # different lane splits change the summation order only
+        np.testing.assert_allclose(part, full[:, :n], rtol=1e-13)
+    # strided view (a shard of a larger (3, N) array) without copying
+    shard = u_all[:, 1000:5000]
+    assert not shard.flags.c_contiguous
+    np.testing.assert_allclose(dm.evaluate(shard, EARTH_20220114, return_comps=True), full[:, 1000:5000],
+                               rtol=1e-13)
+    # host path chunking (> 1 Mi lines of sight -> several pipeline chunks, ragged tail)
+    n_big = (1 << 21) + 12345
+    u_big = fibonacci_sphere(n_big)
+    tot = dm.evaluate(u_big, EARTH_20220114, precision="fp32", out_dtype=np.float32)
+    idx = np.array([0, 1, (1 << 20) - 1, 1 << 20, (1 << 21) - 1, 1 << 21, n_big - 1])
+    ref = oracle.evaluate(model.spec, u_big[:, idx], EARTH_20220114, EARTH_20220114).sum(axis=0)
+    np.testing.assert_allclose(tot[idx], ref, rtol=TOL_FP32)
+    assert np.all(np.isfinite(tot))
+
+
+def test_sharding_invariance_bitwise():
+    """Any contiguous split evaluated separately equals the one-shot result bit for bit when the
+    lane count is the same (reference: nprocesses equality, tests/test_evaluate.py:215-262)."""
+    case, a = golden_case("dirbe_25um_tod_straddle")
+    dm = device_model(case["spec"])
+    n = a["u"].shape[1]
+    flags = dm.outside_flags(a["obs"])  # GLOBAL flags (quirk Q1)
+    one = dm.evaluate(a["u"], a["obs"], a["earth"], return_comps=True, outside_flags=flags)
+    parts = [dm.evaluate(a["u"][:, s], a["obs"][:, s], a["earth"][:, s], return_comps=True,
+                         outside_flags=flags)
+             for s in (slice(0, 100), slice(100, 217), slice(217, n))]
+    np.testing.assert_array_equal(np.concatenate(parts, axis=1), one)
+    # without global flags a shard whose observers stay inside a cutoff differs (documented Q1)
+    local = dm.evaluate(a["u"][:, :100], a["obs"][:, :100], a["earth"][:, :100], return_comps=True)
+    assert local.shape == (6, 100)
+
+
+def test_update_parameters_reuploads():
+    model = zp.Model(zp.Quantity(25.0, "um"))
+    u = fibonacci_sphere(512)
+    before = model.evaluate_xyz(u, EARTH_20220114, return_comps=True)
+    p = model.get_parameters()
+    p["comps"]["cloud"]["n_0"] *= 2.0
+    p["comps"]["band2"]["p"] = 3.5
+    model.update_parameters(p)
+    after = model.evaluate_xyz(u, EARTH_20220114, return_comps=True)
+    np.testing.assert_allclose(after[0], 2.0 * before[0], rtol=1e-13)
+    ref = oracle.evaluate(model.spec, u, EARTH_20220114, EARTH_20220114)
+    assert max_rel_comps(after, ref, floor=COMP_FLOOR_FP64) <= TOL_FP64
+
+
+def test_max_observer_radius_device_and_host():
+    import torch
+
+    case, a = golden_case("dirbe_25um_tod_straddle")
+    dm = device_model(case["spec"])
+    r_host = dm.max_observer_radius(a["obs"])
+    r_dev = dm.max_observer_radius(torch.as_tensor(a["obs"], device="cuda:0"))
+    expect = np.sqrt((a["obs"] ** 2).sum(axis=0)).max()
+    assert r_host == pytest.approx(expect, rel=1e-15) and r_dev == pytest.approx(expect, rel=1e-15)
+    np.testing.assert_array_equal(dm.outside_flags(a["obs"]), oracle.outside_flags(case["spec"], a["obs"]))
+
+
+def test_linearity_in_emissivity_full_size():
+    """Size-independent property at a BASELINE-sized input (nside 512 = 3.1 M lines of sight):
+    scaling every emissivity by k scales the map by k; doubling a component density doubles it."""
+    import torch
+
+    n = 12 * 512 * 512
+    dev = torch.device("cuda:0")
+    u = torch.as_tensor(fibonacci_sphere(n), device=dev)
+    obs = torch.as_tensor(EARTH_20220114, device=dev)
+    model = zp.Model(zp.Quantity(857.0, "GHz"), name="planck18", precision="fp32")
+    base = model.evaluate_xyz(u, obs, return_comps=True, out_dtype=np.float32)
+    p = model.get_parameters()
+    for label in p["emissivities"]:
+        p["emissivities"][label] = tuple(3.0 * v for v in p["emissivities"][label])
+    model.update_parameters(p)
+    scaled = model.evaluate_xyz(u, obs, return_comps=True, out_dtype=np.float32)
+    assert torch.allclose(scaled, 3.0 * base, rtol=2e-6, atol=0.0)
+    assert bool(torch.isfinite(base).all())

@@ -1,0 +1,88 @@
+"""Astropy-side host preparation for ``Model.evaluate`` (imported lazily; needs Astropy).
+
+Ephemerides and frame rotation stay on the Python host by design (BASELINE north star).  This
+follows ``zodipy/bodies.py:16-99`` and ``zodipy/model.py:212-251``: Earth / observer heliocentric
+mean-ecliptic positions (hourly knots + cubic spline for time-ordered data, the SEMB-L2
+approximation) and rotation of the sky coordinates to ``BarycentricMeanEcliptic`` unit vectors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:
+    import astropy.coordinates as coords
+    from astropy import time, units
+except ImportError as err:  # pragma: no cover - astropy is absent from the build image
+    raise ImportError(
+        "Model.evaluate(SkyCoord) needs astropy for ephemerides and frame rotation; "
+        "install astropy or call Model.evaluate_xyz() with ecliptic unit vectors.") from err
+
+MEAN_DIST_TO_L2 = 0.009896235034000056  # AU, zodipy/bodies.py:13
+
+
+def arrange_obstimes(t0: float, t1: float):
+    """Hourly knots spanning the observation (``bodies.py:16-19``)."""
+    dt = 1.0 / 24.0
+    return time.Time(np.arange(t0, t1 + dt, dt), format="mjd")
+
+
+def _body_xyz(body, obstime, ephemeris):
+    return (coords.get_body(body, obstime, ephemeris=ephemeris)
+            .transform_to(coords.HeliocentricMeanEcliptic).cartesian.xyz.to_value(units.AU))
+
+
+def interp_bodypos(body, obstimes_mjd, interp_obstimes, ephemeris):
+    """Cubic-spline interpolation of hourly positions (``bodies.py:22-35``)."""
+    from scipy import interpolate
+
+    pos = _body_xyz(body, interp_obstimes, ephemeris)
+    return interpolate.CubicSpline(interp_obstimes.mjd, pos, axis=-1)(obstimes_mjd)
+
+
+def semb_l2(earthpos):
+    """SEMB-L2 approximation incl. the reference's un-axised norm (``bodies.py:38-50``, Q5)."""
+    dist = np.linalg.norm(earthpos)
+    return earthpos / dist * (dist + MEAN_DIST_TO_L2)
+
+
+def prepare_arrays(skycoord, obspos, obspos_isstr, interp_obstimes, ephemeris):
+    """(earth_xyz, obs_xyz, unit_vectors) as the array seam expects (``model.py:212-251``)."""
+    if interp_obstimes is None:
+        earth_xyz = _body_xyz("earth", skycoord.obstime, ephemeris).flatten()
+    else:
+        earth_xyz = interp_bodypos("earth", skycoord.obstime.mjd, interp_obstimes, ephemeris)
+
+    if obspos_isstr:
+        if obspos == "semb-l2":
+            obs_xyz = semb_l2(earth_xyz)
+        elif obspos == "earth":
+            obs_xyz = earth_xyz
+        elif skycoord.obstime.size == 1:
+            try:
+                obs_xyz = _body_xyz(obspos, skycoord.obstime, ephemeris).flatten()
+            except KeyError as error:
+                valid = [*coords.solar_system_ephemeris.bodies, "semb-l2"]
+                raise ValueError(
+                    f"Invalid observer string: '{obspos}'. Valid observers are: {valid}") from error
+        else:
+            obs_xyz = interp_bodypos(obspos, skycoord.obstime.mjd, interp_obstimes, ephemeris)
+    else:
+        try:
+            obs_xyz = obspos.to_value(units.AU)
+        except units.UnitConversionError as error:
+            raise units.UnitConversionError("The observer position must be in length units.") from error
+
+    if skycoord.obstime.size == 1:
+        obs_xyz = obs_xyz[:, np.newaxis]
+    if earth_xyz.ndim == 1:
+        earth_xyz = earth_xyz[:, np.newaxis]
+
+    ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
+    u_xyz = ecl.cartesian.xyz.value
+    if ecl.isscalar:
+        u_xyz = u_xyz[:, np.newaxis]
+    return earth_xyz, obs_xyz, np.ascontiguousarray(u_xyz)
+
+
+def as_mjy_per_sr(emission):
+    return emission << (units.MJy / units.sr)

@@ -1,0 +1,58 @@
+"""Build the CUDA library in-tree: ``python -m zodipy_b200.build`` -> zodipy_b200/libzodi_b200.so.
+
+sm_100a only (B200).  nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to
+the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libzodi_b200.so")
+SOURCES = ["zodi_capi.cu"]
+HEADERS = ["zodi_device.cuh", "zodi_kernels.cuh", "zodi_model_build.hpp", os.path.join("..", "..", "include", "zodi_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def find_nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; the CUDA library cannot be built")
+    return nvcc
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return LIB_PATH
+    cmd = [find_nvcc(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,535 @@
+// zodi_capi.cu - implementation of the C ABI declared in include/zodi_b200.h.
+//
+// Host side of the library: validates the model descriptor, derives the device-form constants
+// (in double, then narrows for the fp32 kernels), owns the small device buffers of a model
+// handle (blackbody table, quadrature nodes, a pipelined staging workspace for host-memory
+// calls) and launches the kernels of zodi_kernels.cuh.  Only the CUDA runtime is used.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "zodi_kernels.cuh"
+#include "zodi_model_build.hpp"
+
+using namespace zodi;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_CHECK(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(ZODI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+constexpr int kSlots = 3;  // pipeline depth of the host-memory path
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    double* d_in = nullptr;   // u (3 rows) [+ obs (3 rows)] [+ earth (3 rows)], row pitch = chunk
+    void* d_out = nullptr;    // up to ZODI_MAX_COMPS rows
+    bool used = false;
+};
+
+}  // namespace
+
+struct zodi_model_s {
+    int device = 0;
+    zodi_model_desc desc;  // raw copy (pointers nulled)
+    DevModel<double> m64;
+    DevModel<float> m32;
+    Pair<double>* d_table64 = nullptr;
+    Pair<double>* d_nodes64 = nullptr;
+    Pair<float>* d_table32 = nullptr;
+    Pair<float>* d_nodes32 = nullptr;
+    unsigned long long* d_scratch = nullptr;  // 8 bytes for the max-radius reduction
+    // host-memory path workspace
+    std::mutex ws_mutex;
+    Slot slots[kSlots];
+    int64_t ws_chunk = 0;
+    double last_kernel_ms = 0.0;
+};
+
+namespace {
+
+int validate_desc(const zodi_model_desc* d) {
+    if (!d) return fail(ZODI_ERR_INVALID, "model descriptor is NULL");
+    if (d->abi_version != ZODI_ABI_VERSION)
+        return fail(ZODI_ERR_INVALID, "descriptor abi_version %d != library %d", d->abi_version,
+                    ZODI_ABI_VERSION);
+    if (d->kind != ZODI_KELSALL && d->kind != ZODI_RRM)
+        return fail(ZODI_ERR_INVALID, "unknown model kind %d", d->kind);
+    if (d->n_comps < 1 || d->n_comps > ZODI_MAX_COMPS)
+        return fail(ZODI_ERR_INVALID, "n_comps=%d outside [1, %d]", d->n_comps, ZODI_MAX_COMPS);
+    if (d->n_nodes < 1 || d->n_nodes > ZODI_MAX_NODES)
+        return fail(ZODI_ERR_INVALID, "n_nodes=%d outside [1, %d]", d->n_nodes, ZODI_MAX_NODES);
+    if (d->n_temps < 2 || d->n_temps > ZODI_MAX_TEMPS)
+        return fail(ZODI_ERR_INVALID, "n_temps=%d outside [2, %d]", d->n_temps, ZODI_MAX_TEMPS);
+    if (!d->temps || !d->bnu || !d->nodes || !d->weights)
+        return fail(ZODI_ERR_INVALID, "temps/bnu/nodes/weights must be non-NULL");
+    const double dt = (d->temps[d->n_temps - 1] - d->temps[0]) / (d->n_temps - 1);
+    if (!(dt > 0.0)) return fail(ZODI_ERR_INVALID, "table temperatures must be ascending");
+    for (int i = 0; i < d->n_temps; ++i) {
+        const double expect = d->temps[0] + dt * i;
+        if (std::fabs(d->temps[i] - expect) > 1e-9 * std::fabs(d->temps[d->n_temps - 1]))
+            return fail(ZODI_ERR_UNSUPPORTED,
+                        "table temperatures must be uniformly spaced (knot %d = %.17g, expected %.17g)",
+                        i, d->temps[i], expect);
+    }
+    for (int i = 0; i < d->n_comps; ++i)
+        if (n_shape_params(d->comps[i].type) < 0)
+            return fail(ZODI_ERR_INVALID, "component %d has unknown type %d", i, d->comps[i].type);
+    return ZODI_OK;
+}
+
+int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
+    build_dev_model(*d, m->m64);
+    narrow_model(m->m64, m->m32);
+
+    // ---- table as (B_i, B_{i+1}-B_i) pairs, nodes as (x_k, w_k) pairs ----
+    std::vector<Pair<double>> t64, n64;
+    std::vector<Pair<float>> t32, n32;
+    build_pairs(*d, t64, n64, t32, n32);
+    auto put = [](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        if (*dst) { cudaFree(*dst); *dst = nullptr; }
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CU_CHECK(put((void**)&m->d_table64, t64.data(), t64.size() * sizeof(Pair<double>)));
+    CU_CHECK(put((void**)&m->d_nodes64, n64.data(), n64.size() * sizeof(Pair<double>)));
+    CU_CHECK(put((void**)&m->d_table32, t32.data(), t32.size() * sizeof(Pair<float>)));
+    CU_CHECK(put((void**)&m->d_nodes32, n32.data(), n32.size() * sizeof(Pair<float>)));
+    if (!m->d_scratch) CU_CHECK(cudaMalloc((void**)&m->d_scratch, sizeof(unsigned long long)));
+
+    m->desc = *d;
+    m->desc.temps = m->desc.bnu = m->desc.nodes = m->desc.weights = nullptr;
+    return ZODI_OK;
+}
+
+void free_workspace(zodi_model_s* m) {
+    for (Slot& s : m->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.k0) cudaEventDestroy(s.k0);
+        if (s.k1) cudaEventDestroy(s.k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = Slot();
+    }
+    m->ws_chunk = 0;
+}
+
+uint32_t flags_to_mask(const uint8_t* flags, int n_comps) {
+    uint32_t mask = 0;
+    for (int c = 0; c < n_comps; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    return mask;
+}
+
+void flags_from_r(const zodi_model_s* m, double r_max, uint8_t* flags) {
+    for (int c = 0; c < m->desc.n_comps; ++c) {  // r_obs > cutoff, line_of_sight.py:72
+        flags[2 * c] = r_max > m->desc.comps[c].cutoff_inner;
+        flags[2 * c + 1] = r_max > m->desc.comps[c].cutoff_outer;
+    }
+}
+
+int pick_lanes(int64_t n, int n_nodes) {
+    // enough threads to fill 148 SMs x 2048 resident threads; never more lanes than nodes
+    int L = 1;
+    while (L < 32 && n * L < 148 * 2048 && 2 * L <= n_nodes) L *= 2;
+    return L;
+}
+
+template <typename Real, int L>
+cudaError_t launch_generic_L(const DevModel<Real>& M, const LaunchArgs& a, const Pair<Real>* tab,
+                             const Pair<Real>* nodes, cudaStream_t stream) {
+    const int per_cta = kThreads / L;
+    const int64_t grid = (a.n + per_cta - 1) / per_cta;
+    const size_t smem = (size_t)(M.n_temps + M.n_nodes) * sizeof(Pair<Real>);
+    zodi_los_generic_kernel<Real, L><<<(unsigned)grid, kThreads, smem, stream>>>(M, a, tab, nodes);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <typename Real>
+cudaError_t launch_generic(const DevModel<Real>& M, const LaunchArgs& a, const Pair<Real>* tab,
+                           const Pair<Real>* nodes, cudaStream_t stream) {
+    switch (pick_lanes(a.n, M.n_nodes)) {
+        case 1: return launch_generic_L<Real, 1>(M, a, tab, nodes, stream);
+        case 2: return launch_generic_L<Real, 2>(M, a, tab, nodes, stream);
+        case 4: return launch_generic_L<Real, 4>(M, a, tab, nodes, stream);
+        case 8: return launch_generic_L<Real, 8>(M, a, tab, nodes, stream);
+        case 16: return launch_generic_L<Real, 16>(M, a, tab, nodes, stream);
+        default: return launch_generic_L<Real, 32>(M, a, tab, nodes, stream);
+    }
+}
+
+cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
+    if (a.n <= 0) return cudaSuccess;
+    if (precision == ZODI_FP32) return launch_generic<float>(m->m32, a, m->d_table32, m->d_nodes32, stream);
+    return launch_generic<double>(m->m64, a, m->d_table64, m->d_nodes64, stream);
+}
+
+int max_r_device(zodi_model_s* m, const double* d_obs, int64_t n_obs, int64_t stride,
+                 cudaStream_t stream, double* r_max) {
+    CU_CHECK(cudaMemsetAsync(m->d_scratch, 0, sizeof(unsigned long long), stream));
+    const int grid = (int)std::min<int64_t>((n_obs + 255) / 256, 148 * 8);
+    zodi_max_r2_kernel<<<grid, 256, 0, stream>>>(d_obs, n_obs, stride, m->d_scratch);
+    g_launches.fetch_add(1);
+    CU_CHECK(cudaGetLastError());
+    unsigned long long bits = 0;
+    CU_CHECK(cudaMemcpyAsync(&bits, m->d_scratch, sizeof(bits), cudaMemcpyDeviceToHost, stream));
+    CU_CHECK(cudaStreamSynchronize(stream));
+    double r2;
+    std::memcpy(&r2, &bits, sizeof(r2));
+    *r_max = std::sqrt(r2);
+    return ZODI_OK;
+}
+
+double max_r_host(const double* obs, int64_t n_obs, int64_t stride) {
+    double m = 0.0;
+    for (int64_t i = 0; i < n_obs; ++i) {
+        const double x = obs[i], y = obs[stride + i], z = obs[2 * stride + i];
+        m = std::fmax(m, x * x + y * y + z * z);
+    }
+    return std::sqrt(m);
+}
+
+int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
+    if (!m) return fail(ZODI_ERR_INVALID, "model handle is NULL");
+    if (!a) return fail(ZODI_ERR_INVALID, "eval args are NULL");
+    if (a->n < 0) return fail(ZODI_ERR_INVALID, "n=%lld is negative", (long long)a->n);
+    if (a->n == 0) return ZODI_OK;
+    if (!a->u || !a->obs || !a->earth || !a->out)
+        return fail(ZODI_ERR_INVALID, "u/obs/earth/out must be non-NULL");
+    if (a->n_obs != 1 && a->n_obs != a->n)
+        return fail(ZODI_ERR_INVALID, "n_obs=%lld must be 1 or n=%lld", (long long)a->n_obs,
+                    (long long)a->n);
+    if (a->n_earth != 1 && a->n_earth != a->n)
+        return fail(ZODI_ERR_INVALID, "n_earth=%lld must be 1 or n=%lld", (long long)a->n_earth,
+                    (long long)a->n);
+    if (a->u_stride < a->n || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
+        return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
+    if (a->return_comps && a->out_stride < a->n)
+        return fail(ZODI_ERR_INVALID, "out_stride=%lld < n", (long long)a->out_stride);
+    if (a->precision != ZODI_FP64 && a->precision != ZODI_FP32)
+        return fail(ZODI_ERR_INVALID, "unknown precision %d", a->precision);
+    if (a->out_dtype != ZODI_OUT_F64 && a->out_dtype != ZODI_OUT_F32)
+        return fail(ZODI_ERR_INVALID, "unknown out_dtype %d", a->out_dtype);
+    if (a->memory != ZODI_MEM_HOST && a->memory != ZODI_MEM_DEVICE)
+        return fail(ZODI_ERR_INVALID, "unknown memory kind %d", a->memory);
+    return ZODI_OK;
+}
+
+// ---- host-memory path: chunked, 3-deep pipeline H2D | kernel | D2H on private streams ------
+int ensure_workspace(zodi_model_s* m, int64_t chunk) {
+    if (m->ws_chunk >= chunk) return ZODI_OK;
+    free_workspace(m);
+    for (Slot& s : m->slots) {
+        CU_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaEventCreate(&s.k0));
+        CU_CHECK(cudaEventCreate(&s.k1));
+        CU_CHECK(cudaMalloc((void**)&s.d_in, (size_t)chunk * 9 * sizeof(double)));
+        CU_CHECK(cudaMalloc(&s.d_out, (size_t)chunk * ZODI_MAX_COMPS * sizeof(double)));
+    }
+    m->ws_chunk = chunk;
+    return ZODI_OK;
+}
+
+int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask) {
+    std::lock_guard<std::mutex> lock(m->ws_mutex);
+    const int64_t n = a->n;
+    int64_t chunk = 1 << 20;
+    if (n < chunk) chunk = n;
+    int rc = ensure_workspace(m, chunk);
+    if (rc) return rc;
+    chunk = std::min<int64_t>(m->ws_chunk, std::max<int64_t>(chunk, 1));
+    const size_t osz = a->out_dtype == ZODI_OUT_F32 ? sizeof(float) : sizeof(double);
+    const int out_rows = a->return_comps ? m->desc.n_comps : 1;
+    const bool obs_ps = a->n_obs == n && n > 1, earth_ps = a->n_earth == n && n > 1;
+    for (Slot& s : m->slots) s.used = false;
+
+    // single observer / Earth: upload once into slot-independent spots (tail of slot 0 input)
+    // -> simpler: keep them at rows 3..5 / 6..8 of each slot, column 0.
+    int64_t done = 0;
+    int idx = 0;
+    while (done < n) {
+        const int64_t cn = std::min(chunk, n - done);
+        Slot& s = m->slots[idx % kSlots];
+        double* d_u = s.d_in;
+        double* d_obs = s.d_in + 3 * m->ws_chunk;
+        double* d_earth = s.d_in + 6 * m->ws_chunk;
+        const size_t pitch = (size_t)m->ws_chunk * sizeof(double);
+        CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
+                                   (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
+        CU_CHECK(cudaMemcpy2DAsync(d_obs, pitch, a->obs + (obs_ps ? done : 0),
+                                   (size_t)a->obs_stride * sizeof(double),
+                                   (size_t)(obs_ps ? cn : 1) * sizeof(double), 3,
+                                   cudaMemcpyHostToDevice, s.stream));
+        if (m->m64.has_feature)
+            CU_CHECK(cudaMemcpy2DAsync(d_earth, pitch, a->earth + (earth_ps ? done : 0),
+                                       (size_t)a->earth_stride * sizeof(double),
+                                       (size_t)(earth_ps ? cn : 1) * sizeof(double), 3,
+                                       cudaMemcpyHostToDevice, s.stream));
+        LaunchArgs la;
+        la.n = cn;
+        la.u = d_u; la.u_stride = m->ws_chunk;
+        la.obs = d_obs; la.obs_stride = m->ws_chunk; la.obs_per_sample = obs_ps;
+        la.earth = d_earth; la.earth_stride = m->ws_chunk; la.earth_per_sample = earth_ps;
+        la.outside_mask = mask;
+        la.return_comps = a->return_comps;
+        la.out_f32 = a->out_dtype == ZODI_OUT_F32;
+        la.out = s.d_out; la.out_stride = m->ws_chunk;
+        if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
+        CU_CHECK(launch_eval(m, la, a->precision, s.stream));
+        CU_CHECK(cudaEventRecord(s.k1, s.stream));
+        s.used = true;
+        CU_CHECK(cudaMemcpy2DAsync((char*)a->out + (size_t)done * osz,
+                                   (size_t)(a->return_comps ? a->out_stride : n) * osz, s.d_out,
+                                   (size_t)m->ws_chunk * osz, (size_t)cn * osz, out_rows,
+                                   cudaMemcpyDeviceToHost, s.stream));
+        done += cn;
+        ++idx;
+    }
+    double ms_total = 0.0;
+    for (Slot& s : m->slots) {
+        if (!s.used) continue;
+        CU_CHECK(cudaStreamSynchronize(s.stream));
+    }
+    // Kernel-only time: only exact when a single chunk ran per slot; otherwise k0..k1 spans the
+    // slot's whole activity, so report it for single-chunk calls and 0 otherwise.
+    if (idx <= kSlots) {
+        for (Slot& s : m->slots)
+            if (s.used) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) ms_total += ms;
+            }
+    }
+    m->last_kernel_ms = ms_total;
+    return ZODI_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int zodi_abi_version(void) { return ZODI_ABI_VERSION; }
+
+const char* zodi_last_error(void) { return g_last_error.c_str(); }
+
+int zodi_device_count(int* count) {
+    if (!count) return fail(ZODI_ERR_INVALID, "count is NULL");
+    *count = 0;
+    CU_CHECK(cudaGetDeviceCount(count));
+    return ZODI_OK;
+}
+
+int zodi_model_create(const zodi_model_desc* desc, int device, zodi_model_t* out) {
+    if (!out) return fail(ZODI_ERR_INVALID, "out handle pointer is NULL");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    int count = 0;
+    CU_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return fail(ZODI_ERR_CUDA, "device %d not available (%d CUDA devices)", device, count);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    zodi_model_s* m = new (std::nothrow) zodi_model_s();
+    if (!m) return fail(ZODI_ERR_NOMEM, "out of host memory");
+    m->device = device;
+    rc = upload_model(m, desc);
+    if (rc) { zodi_model_destroy(m); return rc; }
+    *out = m;
+    return ZODI_OK;
+}
+
+int zodi_model_update(zodi_model_t m, const zodi_model_desc* desc) {
+    if (!m) return fail(ZODI_ERR_INVALID, "model handle is NULL");
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", m->device);
+    CU_CHECK(cudaDeviceSynchronize());
+    return upload_model(m, desc);
+}
+
+int zodi_model_destroy(zodi_model_t m) {
+    if (!m) return ZODI_OK;
+    {
+        DeviceGuard guard(m->device);
+        cudaDeviceSynchronize();
+        free_workspace(m);
+        cudaFree(m->d_table64); cudaFree(m->d_nodes64);
+        cudaFree(m->d_table32); cudaFree(m->d_nodes32);
+        cudaFree(m->d_scratch);
+    }
+    delete m;
+    return ZODI_OK;
+}
+
+int zodi_flags_from_radius(zodi_model_t m, double r_max, uint8_t* flags) {
+    if (!m || !flags) return fail(ZODI_ERR_INVALID, "NULL argument");
+    flags_from_r(m, r_max, flags);
+    return ZODI_OK;
+}
+
+int zodi_max_observer_radius(zodi_model_t m, const double* obs, int64_t n_obs, int64_t obs_stride,
+                             int32_t memory, void* stream, double* r_max) {
+    if (!m || !obs || !r_max || n_obs < 1 || obs_stride < n_obs)
+        return fail(ZODI_ERR_INVALID, "bad argument");
+    if (memory == ZODI_MEM_HOST) {
+        *r_max = max_r_host(obs, n_obs, obs_stride);
+        return ZODI_OK;
+    }
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", m->device);
+    return max_r_device(m, obs, n_obs, obs_stride, (cudaStream_t)stream, r_max);
+}
+
+int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
+    int rc = check_args(m, a);
+    if (rc) return rc;
+    if (a->n == 0) return ZODI_OK;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", m->device);
+
+    uint8_t flags[2 * ZODI_MAX_COMPS];
+    if (a->outside_flags) {
+        std::memcpy(flags, a->outside_flags, 2 * (size_t)m->desc.n_comps);
+    } else {
+        double r_max = 0.0;
+        if (a->memory == ZODI_MEM_HOST) {
+            r_max = max_r_host(a->obs, a->n_obs, a->obs_stride);
+        } else {
+            rc = max_r_device(m, a->obs, a->n_obs, a->obs_stride, (cudaStream_t)a->stream, &r_max);
+            if (rc) return rc;
+        }
+        flags_from_r(m, r_max, flags);
+    }
+    const uint32_t mask = flags_to_mask(flags, m->desc.n_comps);
+
+    if (a->memory == ZODI_MEM_HOST) return evaluate_host(m, a, mask);
+
+    LaunchArgs la;
+    la.n = a->n;
+    la.u = a->u; la.u_stride = a->u_stride;
+    la.obs = a->obs; la.obs_stride = a->obs_stride; la.obs_per_sample = (a->n_obs == a->n && a->n > 1);
+    la.earth = a->earth; la.earth_stride = a->earth_stride;
+    la.earth_per_sample = (a->n_earth == a->n && a->n > 1);
+    la.outside_mask = mask;
+    la.return_comps = a->return_comps;
+    la.out_f32 = a->out_dtype == ZODI_OUT_F32;
+    la.out = a->out; la.out_stride = a->out_stride;
+    CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
+    return ZODI_OK;
+}
+
+int64_t zodi_kernel_launch_count(void) { return g_launches.load(); }
+
+double zodi_last_kernel_ms(zodi_model_t m) { return m ? m->last_kernel_ms : 0.0; }
+
+int zodi_peak_probe(int device, int32_t kind, double* per_second) {
+    if (!per_second) return fail(ZODI_ERR_INVALID, "per_second is NULL");
+    int count = 0;
+    CU_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(ZODI_ERR_CUDA, "device %d not available", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU_CHECK(cudaEventCreate(&e0));
+    CU_CHECK(cudaEventCreate(&e1));
+    void* buf = nullptr;
+    void* buf2 = nullptr;
+    double best = 0.0;
+    int rc = ZODI_OK;
+    const int64_t copy_bytes = 1ll << 30;
+    if (kind == ZODI_PEAK_HBM_COPY) {
+        if (cudaMalloc(&buf, copy_bytes) != cudaSuccess || cudaMalloc(&buf2, copy_bytes) != cudaSuccess)
+            rc = fail(ZODI_ERR_NOMEM, "cannot allocate copy buffers");
+        else
+            cudaMemset(buf, 1, copy_bytes);
+    } else if (cudaMalloc(&buf, (size_t)blocks * threads * 8) != cudaSuccess) {
+        rc = fail(ZODI_ERR_NOMEM, "cannot allocate probe buffer");
+    }
+    for (int rep = 0; rc == ZODI_OK && rep < 5; ++rep) {
+        const int iters = (kind == ZODI_PEAK_MUFU_EX2) ? 4096 : (kind == ZODI_PEAK_FP64_FMA ? 8192 : 16384);
+        cudaEventRecord(e0);
+        double work = 0.0;
+        switch (kind) {
+            case ZODI_PEAK_FP32_FMA:
+                zodi_peak_fma_kernel<float><<<blocks, threads>>>((float*)buf, iters);
+                work = 2.0 * 64.0 * iters * (double)blocks * threads;
+                break;
+            case ZODI_PEAK_FP64_FMA:
+                zodi_peak_fma_kernel<double><<<blocks, threads>>>((double*)buf, iters);
+                work = 2.0 * 64.0 * iters * (double)blocks * threads;
+                break;
+            case ZODI_PEAK_MUFU_EX2:
+                zodi_peak_mufu_kernel<<<blocks, threads>>>((float*)buf, iters);
+                work = 64.0 * iters * (double)blocks * threads;
+                break;
+            case ZODI_PEAK_HBM_COPY:
+                zodi_peak_copy_kernel<<<blocks * 4, threads>>>((const float4*)buf, (float4*)buf2,
+                                                              copy_bytes / 16);
+                work = 2.0 * (double)copy_bytes;
+                break;
+            default:
+                rc = fail(ZODI_ERR_INVALID, "unknown peak kind %d", kind);
+        }
+        g_launches.fetch_add(1);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            rc = fail(ZODI_ERR_CUDA, "peak probe kernel failed");
+            break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0.f) best = std::max(best, work / (ms * 1e-3));
+    }
+    cudaFree(buf);
+    cudaFree(buf2);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *per_second = best;
+    return rc;
+}
+
+}  // extern "C"

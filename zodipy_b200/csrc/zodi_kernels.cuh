@@ -1,0 +1,146 @@
+// zodi_kernels.cuh - __global__ kernels of the line-of-sight integrator (sm_100a).
+//
+// Mapping: L consecutive lanes (L in {1,2,4,8,16,32}) share one line of sight and split its
+// quadrature nodes (node k -> lane k mod L); partial sums are combined with warp shuffles.
+// L = 1 is thread-per-line-of-sight (no lane idles when n_nodes is not a multiple of L; used for
+// large N), larger L fills the machine when N is small.  Parameters live in the kernel-parameter
+// constant bank (__grid_constant__), the blackbody table and the quadrature nodes are staged in
+// shared memory once per CTA, inputs are read SoA/coalesced and outputs written coalesced.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "zodi_device.cuh"
+
+namespace zodi {
+
+constexpr int kThreads = 256;
+
+// Launch-time arguments (plain pointers; device memory).
+struct LaunchArgs {
+    int64_t n;
+    const double* u;      int64_t u_stride;
+    const double* obs;    int64_t obs_stride;   int obs_per_sample;    // 0: one observer
+    const double* earth;  int64_t earth_stride; int earth_per_sample;
+    uint32_t outside_mask;  // bit 2c: outside inner cutoff of comp c; bit 2c+1: outer
+    int return_comps;
+    int out_f32;
+    void* out;            int64_t out_stride;
+};
+
+template <typename Real>
+__device__ __forceinline__ void store_out(const LaunchArgs& a, int64_t idx, Real v) {
+    if (a.out_f32) reinterpret_cast<float*>(a.out)[idx] = (float)v;
+    else reinterpret_cast<double*>(a.out)[idx] = (double)v;
+}
+
+template <typename Real, int L>
+__device__ __forceinline__ Real lane_group_sum(Real v) {
+#pragma unroll
+    for (int off = L / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Generic kernel: any component list (all reference models incl. RRM and user-edited ones).
+template <typename Real, int L>
+__global__ void __launch_bounds__(kThreads)
+zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
+                        const __grid_constant__ LaunchArgs args,
+                        const Pair<Real>* __restrict__ g_table,
+                        const Pair<Real>* __restrict__ g_nodes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pair<Real>* s_table = reinterpret_cast<Pair<Real>*>(smem_raw);
+    Pair<Real>* s_nodes = s_table + model.n_temps;
+    for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
+    for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    constexpr int kLosPerCta = kThreads / L;
+    const int sub = threadIdx.x % L;
+    const int64_t j = (int64_t)blockIdx.x * kLosPerCta + threadIdx.x / L;
+    const bool active = j < args.n;
+    const int64_t jj = active ? j : args.n - 1;  // keep whole warps converged for the shuffles
+
+    const double ux = args.u[jj], uy = args.u[args.u_stride + jj], uz = args.u[2 * args.u_stride + jj];
+    const int64_t jo = args.obs_per_sample ? jj : 0;
+    const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
+                 oz = args.obs[2 * args.obs_stride + jo];
+    double ex = 0.0, ey = 0.0;
+    if (model.has_feature) {
+        const int64_t je = args.earth_per_sample ? jj : 0;
+        ex = args.earth[je];
+        ey = args.earth[args.earth_stride + je];
+    }
+
+    Real total = Real(0);
+    integrate_line_of_sight<Real>(
+        model, s_table, s_nodes, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, sub, L,
+        [&](int ci, Real part) {
+            const Real v = lane_group_sum<Real, L>(part);
+            total += v;  // component order = model order (emission.sum(axis=0), model.py:203)
+            if (args.return_comps && active && sub == 0)
+                store_out<Real>(args, (int64_t)ci * args.out_stride + j, v);
+        });
+    if (!args.return_comps && active && sub == 0) store_out<Real>(args, j, total);
+}
+
+// max over observers of r^2 = x^2+y^2+z^2 (for the global early-out flags, quirk Q1).
+// Non-negative doubles order like their bit patterns, so atomicMax on the 64-bit pattern works.
+__global__ void zodi_max_r2_kernel(const double* __restrict__ obs, int64_t n, int64_t stride,
+                                   unsigned long long* __restrict__ out_bits) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = obs[i], y = obs[stride + i], z = obs[2 * stride + i];
+        m = fmax(m, x * x + y * y + z * z);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// ---- pipe-peak microbenchmarks (roofline denominators measured on the box) -----------------
+template <typename Real>
+__global__ void zodi_peak_fma_kernel(Real* out, int iters) {
+    Real a0 = Real(threadIdx.x) * Real(1e-3), a1 = a0 + Real(1), a2 = a0 + Real(2), a3 = a0 + Real(3);
+    Real a4 = a0 + Real(4), a5 = a0 + Real(5), a6 = a0 + Real(6), a7 = a0 + Real(7);
+    const Real m = Real(0.9999), c = Real(1e-4);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+            a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+        }
+    }
+    const Real s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == Real(-1)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void zodi_peak_mufu_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f;
+    float a4 = a0 + 0.4f, a5 = a0 + 0.5f, a6 = a0 + 0.6f, a7 = a0 + 0.7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a0));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a1));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a2));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a3));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a4));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a5));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a6));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a7));
+        }
+    }
+    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == -1.0f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void zodi_peak_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                      int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+}  // namespace zodi

@@ -1,0 +1,162 @@
+// zodi_model_build.hpp - pure C++ (no CUDA calls): raw model descriptor -> device-form constants.
+// Shared by the C-ABI implementation (zodi_capi.cu) and the host-emulation debug harness under
+// tests/host_emu (test tool only).
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "zodi_device.cuh"
+
+namespace zodi {
+
+inline int n_shape_params(int type) {
+    switch (type) {
+        case ZODI_CLOUD: return 5;
+        case ZODI_BAND: return 5;
+        case ZODI_RING: return 4;
+        case ZODI_FEATURE: return 6;
+        case ZODI_FAN: return 5;
+        case ZODI_COMET: return 6;
+        case ZODI_INTERSTELLAR: return 1;
+        case ZODI_NARROW_BAND: return 6;
+        case ZODI_BROAD_BAND: return 6;
+        case ZODI_RING_RRM: return 5;
+        case ZODI_FEATURE_RRM: return 7;
+        default: return -1;
+    }
+}
+
+// Raw reference parameters -> constants consumed by density<Real>() (zodi_device.cuh).
+inline void derive_component(const zodi_model_desc& d, const zodi_component_desc& c, double phase_norm,
+                      DevComp<double>& o) {
+    std::memset(&o, 0, sizeof(o));
+    const double* p = c.shape;
+    o.x0 = c.x0[0]; o.y0 = c.x0[1]; o.z0 = c.x0[2];
+    // Z_c = X_c.x sinO sini - X_c.y cosO sini + X_c.z cosi  (e.g. number_density.py:63-67)
+    o.nx = c.sin_Omega * c.sin_i;
+    o.ny = -c.cos_Omega * c.sin_i;
+    o.nz = c.cos_i;
+    o.cut_in = c.cutoff_inner;
+    o.cut_out = c.cutoff_outer;
+    if (d.kind == ZODI_KELSALL) {
+        o.scatter = (c.albedo != 0.0);                       // brightness.py:50
+        o.e1 = (1.0 - c.albedo) * c.emissivity;               // brightness.py:49
+        o.sc = c.albedo * d.solar_irradiance * phase_norm;    // brightness.py:51-54
+        o.T0 = d.T_0;
+        o.mhd = -0.5 * d.delta;
+    } else {
+        o.scatter = 0;
+        o.e1 = d.calibration;                                 // brightness.py:83
+        o.sc = 0.0;
+        o.T0 = c.T_0;                                         // unpack_model.py:123-126
+        o.mhd = -0.5 * c.delta;
+    }
+    switch (c.type) {
+        case ZODI_CLOUD:  // n_0, alpha, beta, gamma, mu
+            o.type = D_CLOUD;
+            o.s[0] = p[0]; o.s[1] = p[4]; o.s[2] = 1.0 / (2.0 * p[4]); o.s[3] = 0.5 * p[4];
+            o.s[4] = -0.5 * p[1]; o.s[5] = -p[2] * kLog2e; o.s[6] = p[3];
+            break;
+        case ZODI_BAND:  // n_0, delta_zeta_rad, v, p, delta_r
+            o.type = D_BAND;
+            o.s[0] = 3.0 * p[0]; o.s[1] = 1.0 / p[1]; o.s[2] = p[3]; o.s[3] = 1.0 / p[2];
+            o.s[4] = 1.0 / p[4]; o.s[5] = (p[3] == 4.0) ? 1.0 : 0.0; o.s[6] = kLog2e;
+            break;
+        case ZODI_RING_RRM:
+        case ZODI_RING:  // n_0, R, sigma_r, sigma_z [, A]
+            o.type = D_RING;
+            o.s[0] = (c.type == ZODI_RING_RRM) ? p[4] * p[0] : p[0];
+            o.s[1] = p[1]; o.s[2] = -kLog2e / (p[2] * p[2]); o.s[3] = -kLog2e / p[3];
+            break;
+        case ZODI_FEATURE_RRM:
+        case ZODI_FEATURE:  // n_0, R, sigma_r, sigma_z, theta_rad, sigma_theta_rad [, A]
+            o.type = D_FEATURE;
+            o.s[0] = (c.type == ZODI_FEATURE_RRM) ? p[6] * p[0] : p[0];
+            o.s[1] = p[1]; o.s[2] = -kLog2e / (p[2] * p[2]); o.s[3] = -kLog2e / p[3];
+            o.s[4] = p[4]; o.s[5] = -kLog2e / (p[5] * p[5]);
+            break;
+        case ZODI_FAN:  // Q, P, gamma, Z_0, R_outer
+            o.type = D_FAN;
+            o.s[0] = -0.5 * p[2]; o.s[1] = 1.0 / p[3]; o.s[2] = -p[1] * kLog2e; o.s[3] = 1.0;
+            o.s[4] = 0.0; o.s[5] = p[4] * p[4]; o.s[6] = p[3]; o.s[7] = p[0];
+            break;
+        case ZODI_COMET:  // gamma, Z_0, P, amp, R_inner, R_outer
+            o.type = D_COMET;
+            o.s[0] = -0.5 * p[0]; o.s[1] = 1.0 / p[1]; o.s[2] = -p[2] * kLog2e; o.s[3] = p[3];
+            o.s[4] = p[4] * p[4]; o.s[5] = p[5] * p[5]; o.s[6] = p[1]; o.s[7] = 0.0;
+            break;
+        case ZODI_INTERSTELLAR:
+            o.type = D_INTERSTELLAR;
+            o.s[0] = p[0];
+            break;
+        case ZODI_NARROW_BAND:  // beta_nb, G, gamma, A, R_inner, R_outer
+            o.type = D_NARROW;
+            o.s[0] = p[0]; o.s[1] = p[1] * kLog2e; o.s[2] = -0.5 * p[2];
+            o.s[3] = p[3] * std::pow(p[5], p[2]); o.s[4] = p[4] * p[4]; o.s[5] = p[5] * p[5];
+            break;
+        case ZODI_BROAD_BAND:  // beta_bb, sigma_bb, gamma, A, R_inner, R_outer
+            o.type = D_BROAD;
+            o.s[0] = p[0]; o.s[1] = 1.0 / p[1]; o.s[2] = -0.5 * p[2];
+            o.s[3] = p[3] * std::pow(p[5], p[2]); o.s[4] = p[4] * p[4]; o.s[5] = p[5] * p[5];
+            o.s[6] = -0.5 * kLog2e;
+            break;
+    }
+}
+
+template <typename To, typename From>
+inline void narrow_model(const DevModel<From>& a, DevModel<To>& b) {
+    std::memset(&b, 0, sizeof(b));
+    b.n_comps = a.n_comps; b.n_nodes = a.n_nodes; b.n_temps = a.n_temps;
+    b.has_feature = a.has_feature;
+    b.t_min = (To)a.t_min; b.inv_dt = (To)a.inv_dt;
+    b.C1 = (To)a.C1; b.C2 = (To)a.C2; b.C3 = (To)a.C3;
+    for (int i = 0; i < a.n_comps; ++i) {
+        const DevComp<From>& s = a.comps[i];
+        DevComp<To>& t = b.comps[i];
+        t.type = s.type; t.scatter = s.scatter;
+        t.x0 = (To)s.x0; t.y0 = (To)s.y0; t.z0 = (To)s.z0;
+        t.nx = (To)s.nx; t.ny = (To)s.ny; t.nz = (To)s.nz;
+        for (int k = 0; k < 8; ++k) t.s[k] = (To)s.s[k];
+        t.e1 = (To)s.e1; t.sc = (To)s.sc; t.T0 = (To)s.T0; t.mhd = (To)s.mhd;
+        t.cut_in = s.cut_in; t.cut_out = s.cut_out;
+    }
+}
+
+
+// Whole model: shared scalars + per-component constants (double).
+inline void build_dev_model(const zodi_model_desc& d, DevModel<double>& M) {
+    std::memset(&M, 0, sizeof(M));
+    M.n_comps = d.n_comps; M.n_nodes = d.n_nodes; M.n_temps = d.n_temps;
+    M.t_min = d.temps[0];
+    M.inv_dt = (d.n_temps - 1) / (d.temps[d.n_temps - 1] - d.temps[0]);
+    M.C1 = d.C1; M.C2 = d.C2; M.C3 = d.C3 * kLog2e;
+    // _get_phase_normalization, scattering.py:53-59
+    const double phase_norm =
+        1.0 / (2.0 * kPi * (2.0 * d.C1 + kPi * d.C2 + (std::exp(d.C3 * kPi) + 1.0) / (d.C3 * d.C3 + 1.0)));
+    M.has_feature = 0;
+    for (int i = 0; i < d.n_comps; ++i) {
+        derive_component(d, d.comps[i], phase_norm, M.comps[i]);
+        if (M.comps[i].type == D_FEATURE) M.has_feature = 1;
+    }
+}
+
+// Blackbody table as (B_i, B_{i+1}-B_i) pairs, quadrature as (x_k, w_k) pairs.
+inline void build_pairs(const zodi_model_desc& d, std::vector<Pair<double>>& t64,
+                        std::vector<Pair<double>>& n64, std::vector<Pair<float>>& t32,
+                        std::vector<Pair<float>>& n32) {
+    t64.resize(d.n_temps); t32.resize(d.n_temps);
+    n64.resize(d.n_nodes); n32.resize(d.n_nodes);
+    for (int i = 0; i < d.n_temps; ++i) {
+        const double b0 = d.bnu[i], b1 = d.bnu[i + 1 < d.n_temps ? i + 1 : i];
+        t64[i] = {b0, b1 - b0};
+        t32[i] = {(float)b0, (float)(b1 - b0)};
+    }
+    for (int i = 0; i < d.n_nodes; ++i) {
+        n64[i] = {d.nodes[i], d.weights[i]};
+        n32[i] = {(float)d.nodes[i], (float)d.weights[i]};
+    }
+}
+
+}  // namespace zodi

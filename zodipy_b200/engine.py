@@ -1,0 +1,193 @@
+"""Handle-level wrapper over the C ABI: one ``DeviceModel`` = one parameter block on one GPU.
+
+This is the array seam of the reference (``zodipy/model.py:253-279``): ecliptic unit vectors
+``(3, N)``, observer and Earth positions ``(3, 1)`` or ``(3, N)`` in, emission ``(ncomps, N)`` or
+``(N,)`` out.  Inputs may be NumPy arrays (host memory: the library stages them through a
+pipelined H2D / kernel / D2H workspace) or torch CUDA tensors (device memory: one asynchronous
+kernel launch on the current torch stream, result stays on the GPU).  torch is only used for
+device memory and streams; the compute is the library's CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .spec import outside_flags as spec_outside_flags
+from .spec import pack_desc
+
+_PRECISIONS = {"fp64": _cabi.FP64, "fp32": _cabi.FP32}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _rows(a, name: str):
+    """(data_ptr, row_length, row_stride) of a (3, n) float64 array with unit inner stride."""
+    if _is_torch(a):
+        import torch
+
+        if a.dtype != torch.float64 or a.dim() != 2 or a.shape[0] != 3:
+            raise ValueError(f"{name} must be a (3, n) float64 tensor")
+        if a.shape[1] > 1 and a.stride(1) != 1:
+            a = a.contiguous()
+        return a, a.data_ptr(), a.shape[1], (a.stride(0) if a.shape[1] > 1 else max(a.stride(0), 1))
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.ndim != 2 or a.shape[0] != 3:
+        raise ValueError(f"{name} must have shape (3, n)")
+    if a.shape[1] > 1 and a.strides[1] != 8:
+        a = np.ascontiguousarray(a)
+    stride = a.strides[0] // 8 if a.shape[1] > 1 else max(a.strides[0] // 8, 1)
+    return a, a.ctypes.data, a.shape[1], stride
+
+
+class DeviceModel:
+    """Device-resident model parameters + the evaluate call."""
+
+    def __init__(self, spec: dict, device: int = 0):
+        self._lib = _cabi.load()
+        self.spec = spec
+        self.device = int(device)
+        self.ncomps = len(spec["comps"])
+        self._handle = C.c_void_p()
+        desc, keep = pack_desc(spec)
+        _cabi.check(self._lib.zodi_model_create(C.byref(desc), self.device, C.byref(self._handle)))
+        del keep
+
+    def update(self, spec: dict) -> None:
+        """Re-upload after ``Model.update_parameters`` (``zodipy/model.py:313-333``)."""
+        desc, keep = pack_desc(spec)
+        _cabi.check(self._lib.zodi_model_update(self._handle, C.byref(desc)))
+        self.spec = spec
+        self.ncomps = len(spec["comps"])
+        del keep
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.zodi_model_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------
+    def max_observer_radius(self, obs) -> float:
+        obs_a, ptr, n_obs, stride = _rows(obs, "obs")
+        out = C.c_double(0.0)
+        if _is_torch(obs_a):
+            import torch
+
+            mem, stream = _cabi.MEM_DEVICE, torch.cuda.current_stream(obs_a.device).cuda_stream
+        else:
+            mem, stream = _cabi.MEM_HOST, None
+        _cabi.check(self._lib.zodi_max_observer_radius(self._handle, ptr, n_obs, stride, mem, stream,
+                                                       C.byref(out)))
+        return out.value
+
+    def outside_flags(self, obs) -> np.ndarray:
+        return spec_outside_flags(self.spec, self.max_observer_radius(obs))
+
+    def evaluate(self, u, obs, earth=None, *, return_comps: bool = False, precision: str = "fp64",
+                 out=None, out_dtype=None, outside_flags=None):
+        """Emission [MJy/sr] for unit vectors ``u`` (3, N).
+
+        ``obs`` / ``earth``: (3,), (3, 1) or (3, N) [AU]; ``earth`` defaults to ``obs``.
+        ``outside_flags``: optional (ncomps, 2) uint8 GLOBAL early-out flags (needed when the
+        observers of a job are sharded over several calls/GPUs); default: derived from ``obs``.
+        Returns an array like the inputs (NumPy -> NumPy, torch CUDA -> torch CUDA) of shape
+        (ncomps, N) if ``return_comps`` else (N,).
+        """
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        if earth is None:
+            earth = obs
+        device_mem = _is_torch(u)
+        u_a, u_ptr, n, u_stride = _rows(u, "unit_vectors")
+        if device_mem:
+            import torch
+
+            if not u_a.is_cuda:
+                raise ValueError("torch inputs must be CUDA tensors (NumPy arrays for host memory)")
+            if u_a.device.index != self.device:
+                raise ValueError(f"inputs are on cuda:{u_a.device.index}, model on cuda:{self.device}")
+            as_dev = lambda a: (a if _is_torch(a) else torch.as_tensor(  # noqa: E731
+                np.asarray(a, dtype=np.float64).reshape(3, -1), device=u_a.device))
+            obs, earth = as_dev(obs), as_dev(earth)
+        obs_a, obs_ptr, n_obs, obs_stride = _rows(obs, "obs")
+        earth_a, earth_ptr, n_earth, earth_stride = _rows(earth, "earth")
+        if n_obs not in (1, n) or n_earth not in (1, n):
+            raise ValueError("obs/earth must hold one position or one per unit vector")
+
+        if out_dtype is None:
+            out_dtype = np.float64
+        out_dtype = np.dtype(out_dtype)
+        if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("out_dtype must be float64 or float32")
+        shape = (self.ncomps, n) if return_comps else (n,)
+        if device_mem:
+            tdtype = torch.float64 if out_dtype == np.float64 else torch.float32
+            if out is None:
+                out = torch.empty(shape, dtype=tdtype, device=u_a.device)
+            elif tuple(out.shape) != shape or out.dtype != tdtype or not out.is_contiguous():
+                raise ValueError("out has wrong shape/dtype or is not contiguous")
+            out_ptr = out.data_ptr()
+            stream = torch.cuda.current_stream(u_a.device).cuda_stream
+        else:
+            if out is None:
+                out = np.empty(shape, dtype=out_dtype)
+            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            out_ptr = out.ctypes.data
+            stream = None
+        if n == 0:
+            return out
+
+        if outside_flags is None:
+            if device_mem and n_obs == 1:
+                # instantaneous observer: avoid a device reduction + sync, read the 3 numbers
+                r = float(torch.linalg.vector_norm(obs_a.reshape(3)).item())
+                flags = spec_outside_flags(self.spec, r)
+            else:
+                flags = self.outside_flags(obs_a)
+        else:
+            flags = np.ascontiguousarray(outside_flags, dtype=np.uint8)
+            if flags.shape != (self.ncomps, 2):
+                raise ValueError(f"outside_flags must have shape ({self.ncomps}, 2)")
+
+        args = _cabi.EvalArgs()
+        args.n = n
+        args.u, args.u_stride = u_ptr, u_stride
+        args.obs, args.n_obs, args.obs_stride = obs_ptr, n_obs, obs_stride
+        args.earth, args.n_earth, args.earth_stride = earth_ptr, n_earth, earth_stride
+        args.outside_flags = flags.ctypes.data_as(_cabi.c_uint8_p)
+        args.return_comps = int(bool(return_comps))
+        args.precision = _PRECISIONS[precision]
+        args.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
+        args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
+        args.out, args.out_stride = out_ptr, n
+        args.stream = stream
+        _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
+        return out
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.zodi_last_kernel_ms(self._handle))
+
+
+def kernel_launch_count() -> int:
+    return int(_cabi.load().zodi_kernel_launch_count())
+
+
+def peak_probe(kind: str, device: int = 0) -> float:
+    """Measured pipe peak on ``device``: 'fp32' / 'fp64' [flop/s], 'mufu' [op/s], 'hbm' [B/s]."""
+    kinds = {"fp32": _cabi.PEAK_FP32_FMA, "fp64": _cabi.PEAK_FP64_FMA,
+             "mufu": _cabi.PEAK_MUFU_EX2, "hbm": _cabi.PEAK_HBM_COPY}
+    out = C.c_double(0.0)
+    _cabi.check(_cabi.load().zodi_peak_probe(int(device), kinds[kind], C.byref(out)))
+    return out.value

@@ -1,0 +1,157 @@
+"""``Model``: the reference's public interface over the B200 line-of-sight integrator.
+
+Signature, argument meaning, output shapes and error behaviour follow
+``zodipy/model.py:33-333``.  The Astropy-side host work of ``Model.evaluate`` (ephemerides, frame
+rotation) is unchanged in spirit and needs Astropy, which is imported lazily; everything below
+the array seam (``zodipy/model.py:253-279``) runs in the CUDA library.  ``evaluate_xyz`` exposes
+that seam directly (no Astropy): it is what the benchmarks, the parity tests and multi-GPU
+sharding use.
+
+Additive, defaulted knobs (not in the reference): ``precision`` ("fp64" faithful | "fp32" fast),
+``device`` (CUDA ordinal; default ``LOCAL_RANK`` or 0).  ``nprocesses`` is accepted for API
+compatibility and ignored: the GPU path has no use for host worker processes.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import spectral
+from . import units as zu
+from .component import ComponentLabel
+from .engine import DeviceModel
+from .spec import build_spec
+from .zodiacal_light_model import clone_model, model_registry
+
+
+class Model:
+    """Main interface (drop-in for ``zodipy.Model``)."""
+
+    def __init__(self, x, *, weights=None, name: str = "dirbe", gauss_quad_degree: int = 50,
+                 extrapolate: bool = False, ephemeris: str = "builtin",
+                 precision: str = "fp64", device: int | None = None) -> None:
+        try:
+            if not x.isscalar and weights is None:
+                raise ValueError("Bandpass weights must be provided for non-scalar `x`.")
+        except AttributeError as error:
+            raise TypeError("The input 'x' must be an astropy Quantity.") from error
+        if not zu.is_quantity(x):
+            raise TypeError("The input 'x' must be an astropy Quantity.")
+        if x.isscalar and weights is not None:
+            raise ValueError("Bandpass weights should not be provided for scalar `x`.")
+
+        self._ipd_model = clone_model(model_registry.get_model(name))
+        if not extrapolate and not self._ipd_model.is_valid_at(x):
+            raise ValueError(
+                "The requested frequencies are outside the valid range of the model. "
+                "If this was intended, set the extrapolate argument to True.")
+
+        if weights is not None:
+            weights = np.asarray(weights, dtype=np.float64)
+            if x.size != weights.size:
+                raise ValueError("Number of wavelengths and weights must be the same in the bandpass.")
+            # normalised over the user's x values in the user's unit (model.py:94; quirk Q6)
+            normalized_weights = weights / spectral.trapezoid(weights, zu.native_value(x))
+        else:
+            normalized_weights = None
+
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        self._x = x
+        self._bounds_error = not extrapolate
+        self._normalized_weights = normalized_weights
+        self._gauss_quad_degree = int(gauss_quad_degree)
+        self._ephemeris = ephemeris
+        self._precision = precision
+        self._device = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
+        self._device_model: DeviceModel | None = None
+        self._init_ipd_model_partials()
+
+    # ---------------------------------------------------------------------------------------
+    def _init_ipd_model_partials(self) -> None:
+        """(Re)build the device parameter block source (``zodipy/model.py:281-301``)."""
+        self._spec = build_spec(self._ipd_model, self._x, self._normalized_weights,
+                                self._bounds_error, self._gauss_quad_degree)
+        self._b_nu_table = self._spec["table"]
+        if self._device_model is not None:
+            self._device_model.update(self._spec)
+
+    @property
+    def spec(self) -> dict:
+        """The neutral model specification uploaded to the device (see ``zodipy_b200.spec``)."""
+        return self._spec
+
+    @property
+    def ncomps(self) -> int:
+        return self._ipd_model.ncomps
+
+    @property
+    def device_model(self) -> DeviceModel:
+        if self._device_model is None:
+            self._device_model = DeviceModel(self._spec, self._device)
+        return self._device_model
+
+    # ---------------------------------------------------------------------------------------
+    def evaluate_xyz(self, unit_vectors, obs_xyz, earth_xyz=None, *, return_comps: bool = False,
+                     precision: str | None = None, out=None, out_dtype=None, outside_flags=None):
+        """The array seam (``zodipy/model.py:253-279,202-203``) without Astropy.
+
+        unit_vectors: (3, N) ecliptic unit vectors; obs_xyz / earth_xyz: (3,), (3, 1) or (3, N)
+        heliocentric ecliptic positions [AU] (``earth_xyz`` defaults to ``obs_xyz``).  NumPy in ->
+        NumPy out; torch CUDA tensors in -> torch CUDA tensor out.  Values are MJy/sr.
+        """
+        return self.device_model.evaluate(
+            unit_vectors, obs_xyz, earth_xyz, return_comps=return_comps,
+            precision=precision or self._precision, out=out, out_dtype=out_dtype,
+            outside_flags=outside_flags)
+
+    def evaluate(self, skycoord, *, obspos="earth", return_comps: bool = False, nprocesses: int = 1):
+        """Simulated zodiacal light [MJy/sr] for an ``astropy.coordinates.SkyCoord``.
+
+        Same contract as ``zodipy/model.py:119-203``.  Requires Astropy at call time.
+        """
+        try:
+            if skycoord.obstime is None:
+                raise ValueError("The `obstime` attribute of the `SkyCoord` object is not set.")
+        except AttributeError as error:
+            raise TypeError("The input coordinates must be an astropy SkyCoord object.") from error
+        try:
+            if not (obspos_isstr := isinstance(obspos, str)) and (
+                (obspos.ndim > 1 and skycoord.obstime.size != obspos.shape[-1])
+                or (obspos.ndim == 1 and skycoord.obstime.size != 1)
+            ):
+                raise ValueError("The number of obstime (ncoords) and obspos (3, ncoords) does not match.")
+        except AttributeError as error:
+            raise TypeError("The observer position is not a string or an astropy Quantity.") from error
+        if skycoord.obstime.size > skycoord.size:
+            raise ValueError("The size of obstime must be either 1 or ncoords.")
+
+        from . import astro  # lazy: needs astropy
+
+        interp_obstimes = None
+        if skycoord.obstime.size != 1:
+            interp_obstimes = astro.arrange_obstimes(skycoord.obstime[0].mjd, skycoord.obstime[-1].mjd)
+        earth_xyz, obs_xyz, u_xyz = astro.prepare_arrays(
+            skycoord, obspos, obspos_isstr, interp_obstimes, self._ephemeris)
+        emission = self.evaluate_xyz(u_xyz, obs_xyz, earth_xyz, return_comps=return_comps)
+        return astro.as_mjy_per_sr(emission)
+
+    # ---------------------------------------------------------------------------------------
+    def get_parameters(self) -> dict:
+        """Model parameter dictionary (``zodipy/model.py:303-310``)."""
+        return self._ipd_model.to_dict()
+
+    def update_parameters(self, parameters: dict) -> None:
+        """Replace the model parameters (``zodipy/model.py:312-333``) and re-upload them."""
+        new = parameters.copy()
+        new["comps"] = {}
+        for key, value in parameters.items():
+            if key == "comps":
+                for comp_key, comp_value in value.items():
+                    label = ComponentLabel(comp_key)
+                    new["comps"][label] = type(self._ipd_model.comps[label])(**comp_value)
+            elif isinstance(value, dict):
+                new[key] = {ComponentLabel(k): v for k, v in value.items()}
+        self._ipd_model = self._ipd_model.__class__(**new)
+        self._init_ipd_model_partials()
