@@ -149,6 +149,10 @@ int zodi_model_destroy(zodi_model_t model);
 /* ---- the hot path ------------------------------------------------------------------------ */
 int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);
 
+/* Name of the kernel family zodi_evaluate launches for this model: "zodi_los_kelsall_kernel"
+ * (fused Kelsall-family kernel) or "zodi_los_generic_kernel" (any component list). */
+const char* zodi_model_kernel_name(zodi_model_t model);
+
 /* Largest heliocentric observer distance sqrt(x^2+y^2+z^2) over (3, n_obs) observers and the
  * resulting early-out flags; used to form the GLOBAL flags when a job is sharded over GPUs
  * (max-reduce r_max over ranks, then zodi_flags_from_radius). */

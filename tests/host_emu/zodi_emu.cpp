@@ -34,6 +34,38 @@ static void run(const zodi_model_desc* d, const DevModel<Real>& M, const std::ve
     }
 }
 
+template <typename Real>
+static void run_kelsall(const KelsallModel<Real>& K, const std::vector<Pair<Real>>& tab,
+                        const std::vector<Pair<Real>>& nodes, int64_t n, const double* u,
+                        const double* obs, int64_t n_obs, const double* earth, int64_t n_earth,
+                        const uint8_t* flags, int lanes, double* out) {
+    uint32_t mask = 0;
+    for (int c = 0; c < K.n_comps; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+        for (int c = 0; c < K.n_comps; ++c) out[c * n + j] = 0.0;
+        auto emit = [&](int ci, Real part) { out[ci * n + j] += (double)part; };
+        for (int sub = 0; sub < lanes; ++sub) {
+#define ZCALL(RF, SC)                                                                             \
+    integrate_kelsall<Real, RF, SC>(K, tab.data(), nodes.data(), u[j], u[n + j], u[2 * n + j],    \
+                                    obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo], earth[je],     \
+                                    earth[n_earth + je], mask, sub, lanes, emit)
+            if (K.n_comps == 6) { if (K.scatter) ZCALL(true, true); else ZCALL(true, false); }
+            else { if (K.scatter) ZCALL(false, true); else ZCALL(false, false); }
+#undef ZCALL
+        }
+    }
+}
+
+// Returns 1 if the Kelsall fast path was eligible and used, 0 if the generic routine ran.
+extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, int lanes, int fast,
+                                      int64_t n, const double* u, const double* obs, int64_t n_obs,
+                                      const double* earth, int64_t n_earth, const uint8_t* flags,
+                                      double* out);
+
 extern "C" int zodi_emu_evaluate(const zodi_model_desc* d, int precision, int lanes, int64_t n,
                                  const double* u, const double* obs, int64_t n_obs,
                                  const double* earth, int64_t n_earth, const uint8_t* flags,
@@ -48,4 +80,26 @@ extern "C" int zodi_emu_evaluate(const zodi_model_desc* d, int precision, int la
     if (precision == ZODI_FP32) run<float>(d, m32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
     else run<double>(d, m64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
     return 0;
+}
+
+extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, int lanes, int fast,
+                                      int64_t n, const double* u, const double* obs, int64_t n_obs,
+                                      const double* earth, int64_t n_earth, const uint8_t* flags,
+                                      double* out) {
+    KelsallModel<double> k64;
+    if (!fast || !build_kelsall_model(*d, k64)) {
+        zodi_emu_evaluate(d, precision, lanes, n, u, obs, n_obs, earth, n_earth, flags, out);
+        return 0;
+    }
+    std::vector<Pair<double>> t64, n64;
+    std::vector<Pair<float>> t32, n32;
+    build_pairs(*d, t64, n64, t32, n32);
+    if (precision == ZODI_FP32) {
+        KelsallModel<float> k32;
+        narrow_kelsall(k64, k32);
+        run_kelsall<float>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+    } else {
+        run_kelsall<double>(k64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+    }
+    return 1;
 }

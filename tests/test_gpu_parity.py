@@ -13,16 +13,41 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp64": (TOL_FP64, COMP_FLOOR_FP64), "fp32": (TOL_FP32, COMP_FLOOR_FP32)}
 
 
-def device_model(spec):
-    return engine.DeviceModel(spec, device=0)
+def device_model(spec, generic=False):
+    """generic=True forces the generic kernel for models the fused Kelsall kernel would take."""
+    import os
+
+    old = os.environ.get("ZODI_FORCE_GENERIC")
+    os.environ["ZODI_FORCE_GENERIC"] = "1" if generic else "0"
+    try:
+        return engine.DeviceModel(spec, device=0)
+    finally:
+        if old is None:
+            os.environ.pop("ZODI_FORCE_GENERIC", None)
+        else:
+            os.environ["ZODI_FORCE_GENERIC"] = old
 
 
+def test_kernel_selection():
+    """Kelsall-family layouts take the fused kernel; RRM and user-edited layouts the generic one."""
+    expect = {"planck18_857": "kelsall", "dirbe_25um_rand": "kelsall", "dirbe_1p25um": "kelsall",
+              "planck13_545": "kelsall", "rrm_60um": "generic", "dirbe_25um_mutated": "generic"}
+    for case_id, which in expect.items():
+        assert device_model(golden_case(case_id)[0]["spec"]).kernel_name == f"zodi_los_{which}_kernel"
+    assert device_model(golden_case("planck18_857")[0]["spec"], generic=True).kernel_name == \
+        "zodi_los_generic_kernel"
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["auto", "generic"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("case_id", case_ids())
-def test_golden_host_memory(case_id, precision):
-    """Committed reference outputs, C-ABI call with HOST buffers (H2D + kernel + D2H)."""
+def test_golden_host_memory(case_id, precision, generic):
+    """Committed reference outputs, C-ABI call with HOST buffers (H2D + kernel + D2H); every case
+    through the kernel the library picks and through the generic kernel."""
     case, a = golden_case(case_id)
-    dm = device_model(case["spec"])
+    dm = device_model(case["spec"], generic=generic)
+    if generic and device_model(case["spec"]).kernel_name == "zodi_los_generic_kernel":
+        pytest.skip("already covered by the auto run")
     launches = engine.kernel_launch_count()
     em = dm.evaluate(a["u"], a["obs"], a["earth"], return_comps=True, precision=precision)
     assert engine.kernel_launch_count() > launches  # the CUDA kernels ran

@@ -75,6 +75,7 @@ SYMBOLS = {
     "zodi_model_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]),
     "zodi_model_update": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc)]),
     "zodi_model_destroy": (C.c_int, [C.c_void_p]),
+    "zodi_model_kernel_name": (C.c_char_p, [C.c_void_p]),
     "zodi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),

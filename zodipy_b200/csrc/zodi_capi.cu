@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -69,6 +70,10 @@ struct zodi_model_s {
     zodi_model_desc desc;  // raw copy (pointers nulled)
     DevModel<double> m64;
     DevModel<float> m32;
+    bool kelsall_ok = false;  // model fits the fused Kelsall-family kernel
+    KelsallModel<double> k64;
+    KelsallModel<float> k32;
+    int force_generic = 0;    // testing knob (ZODI_FORCE_GENERIC=1): always use the generic kernel
     Pair<double>* d_table64 = nullptr;
     Pair<double>* d_nodes64 = nullptr;
     Pair<float>* d_table32 = nullptr;
@@ -116,6 +121,10 @@ int validate_desc(const zodi_model_desc* d) {
 int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     build_dev_model(*d, m->m64);
     narrow_model(m->m64, m->m32);
+    m->kelsall_ok = build_kelsall_model(*d, m->k64);
+    if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
+    const char* fg = std::getenv("ZODI_FORCE_GENERIC");
+    m->force_generic = (fg && fg[0] == '1');
 
     // ---- table as (B_i, B_{i+1}-B_i) pairs, nodes as (x_k, w_k) pairs ----
     std::vector<Pair<double>> t64, n64;
@@ -197,8 +206,43 @@ cudaError_t launch_generic(const DevModel<Real>& M, const LaunchArgs& a, const P
     }
 }
 
+template <typename Real, bool HAS_RF, bool SCATTER, int L>
+cudaError_t launch_kelsall_L(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
+                             const Pair<Real>* nodes, cudaStream_t stream) {
+    const int per_cta = kThreads / L;
+    const int64_t grid = (a.n + per_cta - 1) / per_cta;
+    const size_t smem = (size_t)(K.n_temps + K.n_nodes) * sizeof(Pair<Real>);
+    zodi_los_kelsall_kernel<Real, HAS_RF, SCATTER, L><<<(unsigned)grid, kThreads, smem, stream>>>(K, a, tab, nodes);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <typename Real, bool HAS_RF, bool SCATTER>
+cudaError_t launch_kelsall_RS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
+                              const Pair<Real>* nodes, cudaStream_t stream) {
+    const int L = pick_lanes(a.n, K.n_nodes);
+    if (L == 1) return launch_kelsall_L<Real, HAS_RF, SCATTER, 1>(K, a, tab, nodes, stream);
+    if (L <= 4) return launch_kelsall_L<Real, HAS_RF, SCATTER, 4>(K, a, tab, nodes, stream);
+    return launch_kelsall_L<Real, HAS_RF, SCATTER, 16>(K, a, tab, nodes, stream);
+}
+
+template <typename Real>
+cudaError_t launch_kelsall(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
+                           const Pair<Real>* nodes, cudaStream_t stream) {
+    if (K.n_comps == 6) {
+        if (K.scatter) return launch_kelsall_RS<Real, true, true>(K, a, tab, nodes, stream);
+        return launch_kelsall_RS<Real, true, false>(K, a, tab, nodes, stream);
+    }
+    if (K.scatter) return launch_kelsall_RS<Real, false, true>(K, a, tab, nodes, stream);
+    return launch_kelsall_RS<Real, false, false>(K, a, tab, nodes, stream);
+}
+
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
+    if (m->kelsall_ok && !m->force_generic) {
+        if (precision == ZODI_FP32) return launch_kelsall<float>(m->k32, a, m->d_table32, m->d_nodes32, stream);
+        return launch_kelsall<double>(m->k64, a, m->d_table64, m->d_nodes64, stream);
+    }
     if (precision == ZODI_FP32) return launch_generic<float>(m->m32, a, m->d_table32, m->d_nodes32, stream);
     return launch_generic<double>(m->m64, a, m->d_table64, m->d_nodes64, stream);
 }
@@ -457,6 +501,11 @@ int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
     la.out = a->out; la.out_stride = a->out_stride;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
     return ZODI_OK;
+}
+
+const char* zodi_model_kernel_name(zodi_model_t m) {
+    if (!m) return "";
+    return (m->kelsall_ok && !m->force_generic) ? "zodi_los_kelsall_kernel" : "zodi_los_generic_kernel";
 }
 
 int64_t zodi_kernel_launch_count(void) { return g_launches.load(); }

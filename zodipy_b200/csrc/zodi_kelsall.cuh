@@ -1,0 +1,234 @@
+// zodi_kelsall.cuh - fused integrator specialised for the Kelsall model family.
+//
+// All five Kelsall-type models the reference ships (dirbe, planck13, planck15, planck18, odegard;
+// zodipy/model_registry.py:4-62) have the component list
+//     cloud, band1, band2, band3 [, ring, feature]
+// where cloud and the three bands share one line-of-sight range (cutoffs (eps, 5.2 AU),
+// zodipy/line_of_sight.py:19-26), the bands are centred on the Sun (X_0 = 0,
+// zodipy/component_params.py:32-67) and have p = 4.  For that layout the work per quadrature node
+// that the reference repeats for every component (position, heliocentric distance, grain
+// temperature, blackbody interpolation; zodipy/brightness.py:41-49) is done ONCE and shared by
+// the four densities, the bands share 1/R, constants are merged on the host (log2(e) factors,
+// reciprocals, emissivities), and powers are multiplication chains.  This cuts the executed work
+// from ~60 flops + 7 SFU ops per (pixel x component x node) evaluation (SURVEY.md 8(d) canonical
+// count) to ~27 issue slots + 3.25 SFU ops.  Ring and Feature own their ranges (cutoffs
+// (0.8, 1.2) and (0.7, 1.3) AU) and are integrated in two further node loops.
+//
+// Models that do not fit (user-edited band offsets or p != 4, RRM, ...) use the generic kernel
+// (zodi_device.cuh); eligibility is decided once per model in build_kelsall_model().
+#pragma once
+
+#include <string.h>
+
+#include "zodi_device.cuh"
+
+namespace zodi {
+
+template <typename Real>
+struct KelsallModel {
+    int n_comps;   // 4 or 6
+    int n_nodes;
+    int n_temps;
+    int scatter;   // any albedo != 0
+    int share13;   // band3 uses the same delta_r as band1 -> shares the radial cutoff term
+    // source function
+    Real t_scale;  // T0 / dT           : t = t_scale * 2^(mhd * log2 R^2) + t_ofs  (table coordinate)
+    Real t_ofs;    // -T_min / dT
+    Real t_top;    // n_temps - 1
+    Real mhd;      // -delta / 2
+    Real C1p, C2p, C3l;   // phase function: C1, C2, C3*log2e
+    Real aB[6];    // (1 - albedo_c) * emissivity_c * amplitude_c     (thermal)
+    Real aS[6];    // albedo_c * F_sun * N_phase * amplitude_c        (scattering)
+    // cloud (number_density.py:47-73)
+    Real cx0, cy0, cz0, cnx, cny, cnz;
+    Real c_mu, c_inv2mu, c_halfmu, c_mha, c_mbl, c_gamma;
+    // bands (number_density.py:76-110); normals pre-scaled by log2e^(1/6) / delta_zeta
+    Real bnx[3], bny[3], bnz[3];
+    Real b_c3[3];  // 1 / (v * log2e^(2/3))
+    Real b_y[3];   // log2e^(1/10) / delta_r^2
+    // ring / feature (number_density.py:113-181), both centred on the Sun
+    Real rnx, rny, rnz, r_R, r_c2, r_c3;
+    Real fnx, fny, fnz, f_R, f_c2, f_c3, f_c5, f_theta0;
+    // ranges (always double)
+    double cutA_in, cutA_out, cutR_in, cutR_out, cutF_in, cutF_out;
+};
+
+// --- table lookup -----------------------------------------------------------------------------
+// t = table coordinate (knot units).  fp32: floor via the 2^23 magic constant (stays on the FMA/ALU
+// pipes; FRND/F2I would compete with MUFU for the XU pipe).  round(t - 0.5) differs from floor(t)
+// only when t is an exact integer, where both neighbouring segments give the same value.
+template <typename Real>
+ZODI_HD Real table_at(const Pair<Real>* tab, Real t, Real t_top);
+
+template <>
+ZODI_HD float table_at<float>(const Pair<float>* tab, float t, float t_top) {
+    t = fminf(fmaxf(t, 0.0f), t_top);
+    const float magic = 12582912.0f;     // 1.5 * 2^23: (x + magic) rounds x to an integer
+    const float s = (t - 0.5f) + magic;  // integer-valued: round-half-even(t - 0.5) in [0, t_top]
+#if defined(__CUDA_ARCH__)
+    const int idx = __float_as_int(s) - 0x4B400000;
+#else
+    int bits;
+    memcpy(&bits, &s, 4);
+    const int idx = bits - 0x4B400000;
+#endif
+    // idx may equal t_top (last knot): its stored delta is 0, so B = B_last exactly.
+    const Pair<float> e = tab[idx];
+    return fmaf(e.b, t - (s - magic), e.a);
+}
+
+template <>
+ZODI_HD double table_at<double>(const Pair<double>* tab, double t, double t_top) {
+    t = fmin(fmax(t, 0.0), t_top);
+    const double fl = fmin(floor(t), t_top - 1.0);
+    const Pair<double> e = tab[(int)fl];
+    return fma(e.b, t - fl, e.a);
+}
+
+// Shared per-node source quantities.
+template <typename Real>
+struct NodeSource {
+    Real xh, yh, zh, Rh2, lgR, B, F;  // F = Phi(Theta) / R_h^2 (scattering only)
+};
+
+template <typename Real, bool SCATTER>
+ZODI_HD NodeSource<Real> node_source(const KelsallModel<Real>& K, const Pair<Real>* tab, Real R_los,
+                                     Real ux, Real uy, Real uz, Real ox, Real oy, Real oz) {
+    using M = Math<Real>;
+    NodeSource<Real> s;
+    s.xh = M::fma_(R_los, ux, ox);
+    s.yh = M::fma_(R_los, uy, oy);
+    s.zh = M::fma_(R_los, uz, oz);
+    s.Rh2 = M::fma_(s.xh, s.xh, M::fma_(s.yh, s.yh, s.zh * s.zh));
+    s.lgR = M::log2_(s.Rh2);
+    const Real t = M::fma_(K.t_scale, M::exp2_(K.mhd * s.lgR), K.t_ofs);  // blackbody.py:30
+    s.B = table_at<Real>(tab, t, K.t_top);                                 // brightness.py:48
+    s.F = Real(0);
+    if (SCATTER) {  // brightness.py:50-54, scattering.py:29-50
+        const Real rh_inv = M::rsqrt_(s.Rh2);
+        Real ct = M::fma_(ux, s.xh, M::fma_(uy, s.yh, uz * s.zh)) * rh_inv;
+        ct = M::max_(Real(-1), M::min_(Real(1), ct));
+        const Real th = M::acos_(-ct);
+        s.F = (K.C1p + K.C2p * th + M::exp2_(K.C3l * th)) * rh_inv * rh_inv;
+    }
+    return s;
+}
+
+// exp(-s^6) * (1 + s^4 / v) for one band; (bx,by,bz) is the pre-scaled plane normal.
+template <typename Real>
+ZODI_HD Real band_vertical(Real xh, Real yh, Real zh, Real rinv, Real bx, Real by, Real bz, Real c3) {
+    using M = Math<Real>;
+    const Real sz = M::fma_(xh, bx, M::fma_(yh, by, zh * bz)) * rinv;  // sign irrelevant (even powers)
+    const Real s2 = sz * sz, s4 = s2 * s2;
+    return M::exp2_(-(s4 * s2)) * M::fma_(s4, c3, Real(1));
+}
+
+// 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20)
+template <typename Real>
+ZODI_HD Real band_radial(Real Rh2, Real by) {
+    using M = Math<Real>;
+    const Real y = Rh2 * by;
+    const Real y2 = y * y, y4 = y2 * y2, y5 = y4 * y;
+    return M::one_minus_exp2_neg(y5 * y5);
+}
+
+template <typename Real, bool HAS_RF, bool SCATTER, typename Emit>
+ZODI_HD void integrate_kelsall(const KelsallModel<Real>& K, const Pair<Real>* tab,
+                               const Pair<Real>* nodes, double dux, double duy, double duz,
+                               double dox, double doy, double doz, double dex, double dey,
+                               uint32_t outside_mask, int sub, int L, Emit emit) {
+    using M = Math<Real>;
+    const double r_obs2 = dox * dox + doy * doy + doz * doz;
+    const double bq = ray_bq(dux, duy, duz, dox, doy);
+    const Real ux = Real(dux), uy = Real(duy), uz = Real(duz);
+    const Real ox = Real(dox), oy = Real(doy), oz = Real(doz);
+
+    // ---------------- group A: cloud + band1..3 on one grid --------------------------------
+    {
+        const double start = sphere_distance(bq, r_obs2, K.cutA_in, outside_mask & 1u);
+        const double stop = sphere_distance(bq, r_obs2, K.cutA_out, (outside_mask >> 1) & 1u);
+        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
+        Real aB0 = 0, aB1 = 0, aB2 = 0, aB3 = 0, aS0 = 0, aS1 = 0, aS2 = 0, aS3 = 0;
+        for (int k = sub; k < K.n_nodes; k += L) {
+            const Pair<Real> nw = nodes[k];
+            const NodeSource<Real> s =
+                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
+            // bands: centred on the Sun -> share R
+            const Real rinv = M::rsqrt_(s.Rh2);
+            const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
+            const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
+            const Real rad3 = K.share13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
+            const Real n1 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]) * (rinv * rad1);
+            const Real n2 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]) * (rinv * rad2);
+            const Real n3 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]) * (rinv * rad3);
+            // cloud
+            const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
+            const Real Rc2 = M::fma_(xc, xc, M::fma_(yc, yc, zc * zc));
+            const Real zeta = M::abs_(M::fma_(xc, K.cnx, M::fma_(yc, K.cny, zc * K.cnz))) * M::rsqrt_(Rc2);
+            const Real g = (zeta < K.c_mu) ? zeta * zeta * K.c_inv2mu : zeta - K.c_halfmu;
+            const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
+            const Real n0 = M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
+
+            const Real wB = nw.b * s.B;
+            aB0 = M::fma_(wB, n0, aB0); aB1 = M::fma_(wB, n1, aB1);
+            aB2 = M::fma_(wB, n2, aB2); aB3 = M::fma_(wB, n3, aB3);
+            if (SCATTER) {
+                const Real wF = nw.b * s.F;
+                aS0 = M::fma_(wF, n0, aS0); aS1 = M::fma_(wF, n1, aS1);
+                aS2 = M::fma_(wF, n2, aS2); aS3 = M::fma_(wF, n3, aS3);
+            }
+        }
+        emit(0, h * M::fma_(K.aB[0], aB0, K.aS[0] * aS0));
+        emit(1, h * M::fma_(K.aB[1], aB1, K.aS[1] * aS1));
+        emit(2, h * M::fma_(K.aB[2], aB2, K.aS[2] * aS2));
+        emit(3, h * M::fma_(K.aB[3], aB3, K.aS[3] * aS3));
+    }
+    if (!HAS_RF) return;
+
+    // ---------------- ring (own grid) -----------------------------------------------------------
+    {
+        const double start = sphere_distance(bq, r_obs2, K.cutR_in, (outside_mask >> 8) & 1u);
+        const double stop = sphere_distance(bq, r_obs2, K.cutR_out, (outside_mask >> 9) & 1u);
+        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
+        Real aB = 0, aS = 0;
+        for (int k = sub; k < K.n_nodes; k += L) {
+            const Pair<Real> nw = nodes[k];
+            const NodeSource<Real> s =
+                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
+            const Real d = M::sqrt_(s.Rh2) - K.r_R;
+            const Real Zc = M::fma_(s.xh, K.rnx, M::fma_(s.yh, K.rny, s.zh * K.rnz));
+            const Real n = M::exp2_(M::fma_(d * d, K.r_c2, M::abs_(Zc) * K.r_c3));
+            aB = M::fma_(nw.b * s.B, n, aB);
+            if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
+        }
+        emit(4, h * M::fma_(K.aB[4], aB, K.aS[4] * aS));
+    }
+    // ---------------- feature (own grid) --------------------------------------------------------
+    {
+        const double start = sphere_distance(bq, r_obs2, K.cutF_in, (outside_mask >> 10) & 1u);
+        const double stop = sphere_distance(bq, r_obs2, K.cutF_out, (outside_mask >> 11) & 1u);
+        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
+        // rotate by -(theta_earth + theta_0): then atan2 gives the wrapped longitude offset directly
+        // (number_density.py:163-170; [-pi,pi) vs (-pi,pi] only differs at |delta| = pi where the
+        // squared offset is identical)
+        const double th = atan2(dey, dex) + (double)K.f_theta0;
+        const Real cr = Real(cos(th)), sr = Real(sin(th));
+        Real aB = 0, aS = 0;
+        for (int k = sub; k < K.n_nodes; k += L) {
+            const Pair<Real> nw = nodes[k];
+            const NodeSource<Real> s =
+                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
+            const Real d = M::sqrt_(s.Rh2) - K.f_R;
+            const Real Zc = M::fma_(s.xh, K.fnx, M::fma_(s.yh, K.fny, s.zh * K.fnz));
+            const Real xr = M::fma_(s.xh, cr, s.yh * sr), yr = M::fma_(s.yh, cr, -(s.xh * sr));
+            const Real dth = M::atan2_(yr, xr);
+            const Real e = M::fma_(d * d, K.f_c2, M::fma_(M::abs_(Zc), K.f_c3, dth * dth * K.f_c5));
+            const Real n = M::exp2_(e);
+            aB = M::fma_(nw.b * s.B, n, aB);
+            if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
+        }
+        emit(5, h * M::fma_(K.aB[5], aB, K.aS[5] * aS));
+    }
+}
+
+}  // namespace zodi

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "zodi_device.cuh"
+#include "zodi_kelsall.cuh"
 
 namespace zodi {
 
@@ -78,6 +79,50 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
         [&](int ci, Real part) {
             const Real v = lane_group_sum<Real, L>(part);
             total += v;  // component order = model order (emission.sum(axis=0), model.py:203)
+            if (args.return_comps && active && sub == 0)
+                store_out<Real>(args, (int64_t)ci * args.out_stride + j, v);
+        });
+    if (!args.return_comps && active && sub == 0) store_out<Real>(args, j, total);
+}
+
+// Fused Kelsall-family kernel (zodi_kelsall.cuh): cloud + 3 bands on one shared grid, then ring
+// and feature.  Same thread mapping and staging as the generic kernel.
+template <typename Real, bool HAS_RF, bool SCATTER, int L>
+__global__ void __launch_bounds__(kThreads)
+zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
+                        const __grid_constant__ LaunchArgs args,
+                        const Pair<Real>* __restrict__ g_table,
+                        const Pair<Real>* __restrict__ g_nodes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pair<Real>* s_table = reinterpret_cast<Pair<Real>*>(smem_raw);
+    Pair<Real>* s_nodes = s_table + model.n_temps;
+    for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
+    for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    constexpr int kLosPerCta = kThreads / L;
+    const int sub = threadIdx.x % L;
+    const int64_t j = (int64_t)blockIdx.x * kLosPerCta + threadIdx.x / L;
+    const bool active = j < args.n;
+    const int64_t jj = active ? j : args.n - 1;
+
+    const double ux = args.u[jj], uy = args.u[args.u_stride + jj], uz = args.u[2 * args.u_stride + jj];
+    const int64_t jo = args.obs_per_sample ? jj : 0;
+    const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
+                 oz = args.obs[2 * args.obs_stride + jo];
+    double ex = 0.0, ey = 0.0;
+    if (HAS_RF) {
+        const int64_t je = args.earth_per_sample ? jj : 0;
+        ex = args.earth[je];
+        ey = args.earth[args.earth_stride + je];
+    }
+
+    Real total = Real(0);
+    integrate_kelsall<Real, HAS_RF, SCATTER>(
+        model, s_table, s_nodes, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, sub, L,
+        [&](int ci, Real part) {
+            const Real v = lane_group_sum<Real, L>(part);
+            total += v;
             if (args.return_comps && active && sub == 0)
                 store_out<Real>(args, (int64_t)ci * args.out_stride + j, v);
         });

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "zodi_device.cuh"
+#include "zodi_kelsall.cuh"
 
 namespace zodi {
 
@@ -157,6 +158,92 @@ inline void build_pairs(const zodi_model_desc& d, std::vector<Pair<double>>& t64
         n64[i] = {d.nodes[i], d.weights[i]};
         n32[i] = {(float)d.nodes[i], (float)d.weights[i]};
     }
+}
+
+// Kelsall-family fast path: returns false if the model does not have the layout the fused
+// kernel assumes (then the generic kernel is used).  See zodi_kelsall.cuh.
+inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& K) {
+    std::memset(&K, 0, sizeof(K));
+    if (d.kind != ZODI_KELSALL) return false;
+    if (d.n_comps != 4 && d.n_comps != 6) return false;
+    const zodi_component_desc* c = d.comps;
+    if (c[0].type != ZODI_CLOUD) return false;
+    for (int b = 1; b <= 3; ++b) {
+        if (c[b].type != ZODI_BAND) return false;
+        if (c[b].x0[0] != 0.0 || c[b].x0[1] != 0.0 || c[b].x0[2] != 0.0) return false;  // share R
+        if (c[b].shape[3] != 4.0) return false;                                          // p == 4
+        if (c[b].cutoff_inner != c[0].cutoff_inner || c[b].cutoff_outer != c[0].cutoff_outer)
+            return false;                                                                // one grid
+        if (!(c[b].shape[1] > 0.0) || !(c[b].shape[2] != 0.0) || !(c[b].shape[4] > 0.0)) return false;
+    }
+    if (d.n_comps == 6) {
+        if (c[4].type != ZODI_RING || c[5].type != ZODI_FEATURE) return false;
+        for (int r = 4; r <= 5; ++r)
+            if (c[r].x0[0] != 0.0 || c[r].x0[1] != 0.0 || c[r].x0[2] != 0.0) return false;
+    }
+    K.n_comps = d.n_comps; K.n_nodes = d.n_nodes; K.n_temps = d.n_temps;
+    const double dt = (d.temps[d.n_temps - 1] - d.temps[0]) / (d.n_temps - 1);
+    K.t_scale = d.T_0 / dt;
+    K.t_ofs = -d.temps[0] / dt;
+    K.t_top = d.n_temps - 1;
+    K.mhd = -0.5 * d.delta;
+    K.C1p = d.C1; K.C2p = d.C2; K.C3l = d.C3 * kLog2e;
+    const double phase_norm =
+        1.0 / (2.0 * kPi * (2.0 * d.C1 + kPi * d.C2 + (std::exp(d.C3 * kPi) + 1.0) / (d.C3 * d.C3 + 1.0)));
+    K.scatter = 0;
+    for (int i = 0; i < d.n_comps; ++i) {
+        const double amp = (c[i].type == ZODI_BAND ? 3.0 : 1.0) * c[i].shape[0];  // n_0 (3 n_0 for bands)
+        K.aB[i] = (1.0 - c[i].albedo) * c[i].emissivity * amp;   // brightness.py:49
+        K.aS[i] = c[i].albedo * d.solar_irradiance * phase_norm * amp;  // brightness.py:51-54
+        if (c[i].albedo != 0.0) K.scatter = 1;
+    }
+    // cloud: n_0, alpha, beta, gamma, mu
+    K.cx0 = c[0].x0[0]; K.cy0 = c[0].x0[1]; K.cz0 = c[0].x0[2];
+    K.cnx = c[0].sin_Omega * c[0].sin_i; K.cny = -c[0].cos_Omega * c[0].sin_i; K.cnz = c[0].cos_i;
+    K.c_mu = c[0].shape[4]; K.c_inv2mu = 1.0 / (2.0 * c[0].shape[4]); K.c_halfmu = 0.5 * c[0].shape[4];
+    K.c_mha = -0.5 * c[0].shape[1]; K.c_mbl = -c[0].shape[2] * kLog2e; K.c_gamma = c[0].shape[3];
+    // bands: n_0, delta_zeta_rad, v, p, delta_r
+    const double l6 = std::pow(kLog2e, 1.0 / 6.0), l23 = std::pow(kLog2e, 2.0 / 3.0),
+                 l10 = std::pow(kLog2e, 0.1);
+    for (int b = 0; b < 3; ++b) {
+        const zodi_component_desc& q = c[b + 1];
+        const double sc = l6 / q.shape[1];
+        K.bnx[b] = q.sin_Omega * q.sin_i * sc; K.bny[b] = -q.cos_Omega * q.sin_i * sc; K.bnz[b] = q.cos_i * sc;
+        K.b_c3[b] = 1.0 / (q.shape[2] * l23);
+        K.b_y[b] = l10 / (q.shape[4] * q.shape[4]);
+    }
+    K.share13 = (c[1].shape[4] == c[3].shape[4]);
+    K.cutA_in = c[0].cutoff_inner; K.cutA_out = c[0].cutoff_outer;
+    if (d.n_comps == 6) {
+        const zodi_component_desc& r = c[4];  // n_0, R, sigma_r, sigma_z
+        K.rnx = r.sin_Omega * r.sin_i; K.rny = -r.cos_Omega * r.sin_i; K.rnz = r.cos_i;
+        K.r_R = r.shape[1]; K.r_c2 = -kLog2e / (r.shape[2] * r.shape[2]); K.r_c3 = -kLog2e / r.shape[3];
+        K.cutR_in = r.cutoff_inner; K.cutR_out = r.cutoff_outer;
+        const zodi_component_desc& f = c[5];  // n_0, R, sigma_r, sigma_z, theta_rad, sigma_theta_rad
+        K.fnx = f.sin_Omega * f.sin_i; K.fny = -f.cos_Omega * f.sin_i; K.fnz = f.cos_i;
+        K.f_R = f.shape[1]; K.f_c2 = -kLog2e / (f.shape[2] * f.shape[2]); K.f_c3 = -kLog2e / f.shape[3];
+        K.f_theta0 = f.shape[4]; K.f_c5 = -kLog2e / (f.shape[5] * f.shape[5]);
+        K.cutF_in = f.cutoff_inner; K.cutF_out = f.cutoff_outer;
+    }
+    return true;
+}
+
+template <typename To, typename From>
+inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
+    std::memset(&b, 0, sizeof(b));
+    b.n_comps = a.n_comps; b.n_nodes = a.n_nodes; b.n_temps = a.n_temps;
+    b.scatter = a.scatter; b.share13 = a.share13;
+#define ZN(f) b.f = (To)a.f
+    ZN(t_scale); ZN(t_ofs); ZN(t_top); ZN(mhd); ZN(C1p); ZN(C2p); ZN(C3l);
+    for (int i = 0; i < 6; ++i) { ZN(aB[i]); ZN(aS[i]); }
+    ZN(cx0); ZN(cy0); ZN(cz0); ZN(cnx); ZN(cny); ZN(cnz);
+    ZN(c_mu); ZN(c_inv2mu); ZN(c_halfmu); ZN(c_mha); ZN(c_mbl); ZN(c_gamma);
+    for (int i = 0; i < 3; ++i) { ZN(bnx[i]); ZN(bny[i]); ZN(bnz[i]); ZN(b_c3[i]); ZN(b_y[i]); }
+    ZN(rnx); ZN(rny); ZN(rnz); ZN(r_R); ZN(r_c2); ZN(r_c3);
+    ZN(fnx); ZN(fny); ZN(fnz); ZN(f_R); ZN(f_c2); ZN(f_c3); ZN(f_c5); ZN(f_theta0);
+#undef ZN
+    b.cutA_in = a.cutA_in; b.cutA_out = a.cutA_out; b.cutR_in = a.cutR_in; b.cutR_out = a.cutR_out;
+    b.cutF_in = a.cutF_in; b.cutF_out = a.cutF_out;
 }
 
 }  // namespace zodi

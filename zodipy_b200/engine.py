@@ -176,6 +176,10 @@ class DeviceModel:
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 
+    @property
+    def kernel_name(self) -> str:
+        return self._lib.zodi_model_kernel_name(self._handle).decode()
+
     def last_kernel_ms(self) -> float:
         return float(self._lib.zodi_last_kernel_ms(self._handle))
 
