@@ -46,17 +46,21 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nside", type=int, default=2048)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused peer-store epilogue (default) or separate NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def workload_config(nside, n_gpus, precision):
+def workload_config(nside, n_gpus, precision, gather="fused"):
     return {"workload": f"{MODEL_NAME} {X_GHZ:g} GHz, HEALPix nside={nside} full-sky map "
                         f"({12 * nside * nside} lines of sight x 4 comps x {DEG} nodes), single obstime, "
                         "observer=earth (BASELINE configs[2])",
             "precision_mode": precision, "nside": nside, "n_los": 12 * nside * nside, "ncomps": 4,
-            "gauss_quad_degree": DEG, "sharding": f"contiguous x{n_gpus} + allgather",
+            "gauss_quad_degree": DEG,
+            "sharding": (f"contiguous x{n_gpus}, " + ("kernel epilogue stores to all peers' maps (NVLink P2P)"
+                         if gather == "fused" else "NCCL all-gather")) if n_gpus > 1 else "single GPU",
             "l2": "inputs (24 B/line of sight, >= 1.2 GB per step at 1 GPU) exceed the 126 MB L2"}
 
 
@@ -223,7 +227,16 @@ def run_b200(args):
     out_local = torch.empty(n_local, dtype=tdtype, device=dev)
     torch.cuda.synchronize()
 
+    # N > 1: the kernel stores its slice into every rank's full map (fused all-gather over NVLink
+    # peer memory); --gather nccl uses a separate NCCL all-gather instead.
+    fused = world > 1 and args.gather == "fused"
+    peer_map = sharding.PeerMap(npix, 1, out_dtype, local_rank) if fused else None
+
     def step():
+        if fused:
+            dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out_dtype=out_dtype,
+                        outside_flags=flags, peer_map=peer_map)
+            return peer_map.finish()
         dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
                     outside_flags=flags)
         if world > 1:
@@ -253,15 +266,27 @@ def run_b200(args):
     e0.record()
     for i in range(args.steps):
         k_events[i][0].record()
-        dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
-                    outside_flags=flags)
+        if fused:
+            dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out_dtype=out_dtype,
+                        outside_flags=flags, peer_map=peer_map)
+        else:
+            dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
+                        outside_flags=flags)
         k_events[i][1].record()
-        if world > 1:
+        if fused:
+            full = peer_map.finish()
+        elif world > 1:
             full = sharding.allgather_map(out_local, npix)
     e1.record()
     barrier()
     launches = engine.kernel_launch_count() - launches0
     elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        # every rank must hold the complete map: compare with an independent NCCL all-gather
+        dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
+                    outside_flags=flags)
+        check = sharding.allgather_map(out_local, npix)
+        assert torch.equal(full, check), "assembled map differs from the all-gathered reference"
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
     if world > 1:
         t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -297,6 +322,9 @@ def run_b200(args):
         assert np.array_equal(out_np, out_local.cpu().numpy()), "host-path result differs from device path"
 
     if rank != 0:
+        if peer_map is not None:
+            dist.barrier()
+            peer_map.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -360,13 +388,16 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f64",
-        "data": "synthetic", "config": workload_config(args.nside, world, precision),
+        "data": "synthetic", "config": workload_config(args.nside, world, precision, args.gather),
         "pixels_per_s": npix / (ms_per_step * 1e-3),
         "max_rel_err_vs_oracle": max_rel, "tolerance": 1e-5 if precision == "fp32" else 1e-10,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu, "fp64_mode": fp64,
     }
     print(json.dumps(line))
+    if peer_map is not None:
+        dist.barrier()
+        peer_map.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,11 +30,13 @@
 extern "C" {
 #endif
 
-#define ZODI_ABI_VERSION 1
+#define ZODI_ABI_VERSION 2
 #define ZODI_MAX_COMPS 16   /* reference models have 4, 6 or 8 components */
 #define ZODI_MAX_NODES 1024 /* gauss_quad_degree upper bound (reference default: 50) */
 #define ZODI_MAX_TEMPS 1024 /* blackbody table knots (reference: 100, zodipy/blackbody.py:11) */
 #define ZODI_N_SHAPE 8
+#define ZODI_MAX_PEERS 8        /* GPUs of one NVSwitch box */
+#define ZODI_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 typedef enum {
     ZODI_OK = 0,
@@ -134,6 +136,17 @@ typedef struct {
     int64_t out_stride; /* row stride of out in elements when return_comps (>= n) */
     void* stream;       /* cudaStream_t for ZODI_MEM_DEVICE (NULL = default stream); async.
                            ZODI_MEM_HOST calls are synchronous and ignore it. */
+    /* Fused all-gather (ZODI_MEM_DEVICE only): when n_peers > 0 the kernel epilogue stores element
+     * j of this call (component row c) to peer_out[p][c * peer_stride + peer_offset + j] for every
+     * p < n_peers - the map buffers of all GPUs of the box (own buffer included), mapped with
+     * zodi_peer_buffer_open - so the slice a rank computes lands in every rank's full map while
+     * the kernel is still running; `out` is then ignored and may be NULL.  This replaces the
+     * np.concatenate of the reference's worker results (zodipy/model.py:198). */
+    int32_t n_peers;
+    int32_t reserved;
+    void* peer_out[ZODI_MAX_PEERS];
+    int64_t peer_offset;
+    int64_t peer_stride;
 } zodi_eval_args;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -159,6 +172,14 @@ const char* zodi_model_kernel_name(zodi_model_t model);
 int zodi_max_observer_radius(zodi_model_t model, const double* obs, int64_t n_obs,
                              int64_t obs_stride, int32_t memory, void* stream, double* r_max);
 int zodi_flags_from_radius(zodi_model_t model, double r_max, uint8_t* flags /* (n_comps,2) */);
+
+/* ---- peer-visible map buffers (one process per GPU; CUDA IPC over NVLink/NVSwitch) ----------
+ * alloc: cudaMalloc on `device` + export handle; open: map another process's buffer into this
+ * process (peer access is enabled lazily); close/free undo them. */
+int zodi_peer_buffer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle[ZODI_IPC_HANDLE_BYTES]);
+int zodi_peer_buffer_open(int device, const uint8_t handle[ZODI_IPC_HANDLE_BYTES], void** ptr);
+int zodi_peer_buffer_close(int device, void* ptr);
+int zodi_peer_buffer_free(int device, void* ptr);
 
 /* ---- measurement support ------------------------------------------------------------------ */
 typedef enum {

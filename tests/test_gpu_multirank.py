@@ -1,0 +1,121 @@
+"""Sharded evaluation with real kernels.
+
+* Any box (1 GPU): two processes share cuda:0, rendezvous over gloo; the sharded map must be
+  bit-identical to the single-process map (reference: nprocesses equality,
+  tests/test_evaluate.py:215-262).
+* Boxes with >= 2 GPUs: one process per GPU over NCCL; the fused peer-store epilogue
+  (kernel writes its slice into every rank's map over NVLink) must equal the NCCL all-gather.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, backend, case_id, per_sample, precision, use_peer_map, queue):
+    import torch
+    import torch.distributed as dist
+
+    from helpers import golden_case
+    from zodipy_b200 import engine, sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev_index = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case, a = golden_case(case_id)
+        n = a["u"].shape[1]
+        lo, hi = sharding.split_bounds(n, world)[rank]
+        dm = engine.DeviceModel(case["spec"], device=dev_index)
+        u = torch.as_tensor(np.ascontiguousarray(a["u"][:, lo:hi]), device=dev)
+        obs = torch.as_tensor(np.ascontiguousarray(a["obs"][:, lo:hi] if per_sample else a["obs"]), device=dev)
+        earth = torch.as_tensor(np.ascontiguousarray(a["earth"][:, lo:hi] if per_sample else a["earth"]),
+                                device=dev)
+        full = sharding.evaluate_sharded(
+            dm.evaluate, dm.max_observer_radius, lambda r: sharding_flags(dm, r), u, obs, earth, n,
+            obs_per_sample=per_sample, return_comps=True, precision=precision)
+        result = {"gathered": full.cpu().numpy()}
+        if use_peer_map:
+            pm = sharding.PeerMap(n, dm.ncomps, np.float64, dev_index)
+            r_glob = sharding.global_max_radius(dm.max_observer_radius(obs)) if per_sample else \\
+                dm.max_observer_radius(obs)
+            dm.evaluate(u, obs, earth, return_comps=True, precision=precision,
+                        outside_flags=sharding_flags(dm, r_glob), peer_map=pm)
+            result["fused"] = pm.finish().cpu().numpy()
+            dist.barrier()
+            pm.close()
+        queue.put((rank, result))
+    except Exception as err:
+        queue.put((rank, err))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def sharding_flags(dm, r_max):
+    from zodipy_b200.spec import outside_flags
+
+    return outside_flags(dm.spec, r_max)
+
+
+def _run(world, backend, case_id, per_sample, precision, use_peer_map):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, case_id, per_sample, precision,
+                                               use_peer_map, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for r, v in results.items():
+        assert not isinstance(v, Exception), f"rank {r}: {v!r}"
+    return results
+
+
+@pytest.mark.parametrize("case_id,per_sample", [("dirbe_25um_tod_straddle", True), ("planck18_857", False),
+                                                ("rrm_60um", False)])
+def test_two_processes_one_gpu_bitwise(case_id, per_sample):
+    from helpers import golden_case
+    from zodipy_b200 import engine
+
+    case, a = golden_case(case_id)
+    single = engine.DeviceModel(case["spec"], 0).evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
+    results = _run(2, "gloo", case_id, per_sample, "fp64", False)
+    for r in range(2):
+        np.testing.assert_array_equal(results[r]["gathered"], single)
+
+
+@pytest.mark.parametrize("case_id,per_sample", [("dirbe_25um_tod_straddle", True), ("planck18_857", False)])
+def test_fused_peer_store_equals_allgather(case_id, per_sample):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    from helpers import golden_case
+    from zodipy_b200 import engine
+
+    world = min(torch.cuda.device_count(), 4)
+    case, a = golden_case(case_id)
+    single = engine.DeviceModel(case["spec"], 0).evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
+    results = _run(world, "nccl", case_id, per_sample, "fp64", True)
+    for r in range(world):
+        np.testing.assert_array_equal(results[r]["gathered"], single)
+        np.testing.assert_array_equal(results[r]["fused"], single)

@@ -10,11 +10,13 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_COMPS = 16
 MAX_NODES = 1024
 MAX_TEMPS = 1024
 N_SHAPE = 8
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 
 KELSALL, RRM = 0, 1
 FP64, FP32 = 0, 1
@@ -64,6 +66,9 @@ class EvalArgs(C.Structure):
         ("out_dtype", C.c_int32), ("memory", C.c_int32),
         ("out", C.c_void_p), ("out_stride", C.c_int64),
         ("stream", C.c_void_p),
+        ("n_peers", C.c_int32), ("reserved", C.c_int32),
+        ("peer_out", C.c_void_p * MAX_PEERS),
+        ("peer_offset", C.c_int64), ("peer_stride", C.c_int64),
     ]
 
 
@@ -80,6 +85,10 @@ SYMBOLS = {
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),
     "zodi_flags_from_radius": (C.c_int, [C.c_void_p, C.c_double, c_uint8_p]),
+    "zodi_peer_buffer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), c_uint8_p]),
+    "zodi_peer_buffer_open": (C.c_int, [C.c_int, c_uint8_p, C.POINTER(C.c_void_p)]),
+    "zodi_peer_buffer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "zodi_peer_buffer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "zodi_peak_probe": (C.c_int, [C.c_int, C.c_int32, c_double_p]),
     "zodi_kernel_launch_count": (C.c_int64, []),
     "zodi_last_kernel_ms": (C.c_double, [C.c_void_p]),

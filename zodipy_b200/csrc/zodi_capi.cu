@@ -277,7 +277,17 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
     if (!a) return fail(ZODI_ERR_INVALID, "eval args are NULL");
     if (a->n < 0) return fail(ZODI_ERR_INVALID, "n=%lld is negative", (long long)a->n);
     if (a->n == 0) return ZODI_OK;
-    if (!a->u || !a->obs || !a->earth || !a->out)
+    if (a->n_peers < 0 || a->n_peers > ZODI_MAX_PEERS)
+        return fail(ZODI_ERR_INVALID, "n_peers=%d outside [0, %d]", a->n_peers, ZODI_MAX_PEERS);
+    if (a->n_peers > 0) {
+        if (a->memory != ZODI_MEM_DEVICE)
+            return fail(ZODI_ERR_INVALID, "peer output needs ZODI_MEM_DEVICE inputs");
+        for (int p = 0; p < a->n_peers; ++p)
+            if (!a->peer_out[p]) return fail(ZODI_ERR_INVALID, "peer_out[%d] is NULL", p);
+        if (a->peer_offset < 0 || (a->return_comps && a->peer_stride < a->peer_offset + a->n))
+            return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
+    }
+    if (!a->u || !a->obs || !a->earth || (!a->out && a->n_peers == 0))
         return fail(ZODI_ERR_INVALID, "u/obs/earth/out must be non-NULL");
     if (a->n_obs != 1 && a->n_obs != a->n)
         return fail(ZODI_ERR_INVALID, "n_obs=%lld must be 1 or n=%lld", (long long)a->n_obs,
@@ -287,7 +297,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
                     (long long)a->n);
     if (a->u_stride < a->n || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
         return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
-    if (a->return_comps && a->out_stride < a->n)
+    if (a->return_comps && a->n_peers == 0 && a->out_stride < a->n)
         return fail(ZODI_ERR_INVALID, "out_stride=%lld < n", (long long)a->out_stride);
     if (a->precision != ZODI_FP64 && a->precision != ZODI_FP32)
         return fail(ZODI_ERR_INVALID, "unknown precision %d", a->precision);
@@ -357,6 +367,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask) {
         la.return_comps = a->return_comps;
         la.out_f32 = a->out_dtype == ZODI_OUT_F32;
         la.out = s.d_out; la.out_stride = m->ws_chunk;
+        la.n_peers = 0; la.peer_offset = 0; la.peer_stride = 0;
         if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
         CU_CHECK(launch_eval(m, la, a->precision, s.stream));
         CU_CHECK(cudaEventRecord(s.k1, s.stream));
@@ -499,6 +510,8 @@ int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
     la.return_comps = a->return_comps;
     la.out_f32 = a->out_dtype == ZODI_OUT_F32;
     la.out = a->out; la.out_stride = a->out_stride;
+    la.n_peers = a->n_peers; la.peer_offset = a->peer_offset; la.peer_stride = a->peer_stride;
+    for (int p = 0; p < ZODI_MAX_PEERS; ++p) la.peer_out[p] = p < a->n_peers ? a->peer_out[p] : nullptr;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
     return ZODI_OK;
 }
@@ -506,6 +519,50 @@ int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
 const char* zodi_model_kernel_name(zodi_model_t m) {
     if (!m) return "";
     return (m->kelsall_ok && !m->force_generic) ? "zodi_los_kelsall_kernel" : "zodi_los_generic_kernel";
+}
+
+int zodi_peer_buffer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle[ZODI_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == ZODI_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ptr || !handle || bytes <= 0) return fail(ZODI_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    *ptr = nullptr;
+    CU_CHECK(cudaMalloc(ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return fail(ZODI_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    std::memcpy(handle, &h, sizeof(h));
+    return ZODI_OK;
+}
+
+int zodi_peer_buffer_open(int device, const uint8_t handle[ZODI_IPC_HANDLE_BYTES], void** ptr) {
+    if (!ptr || !handle) return fail(ZODI_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CU_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ZODI_OK;
+}
+
+int zodi_peer_buffer_close(int device, void* ptr) {
+    if (!ptr) return ZODI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    CU_CHECK(cudaIpcCloseMemHandle(ptr));
+    return ZODI_OK;
+}
+
+int zodi_peer_buffer_free(int device, void* ptr) {
+    if (!ptr) return ZODI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    CU_CHECK(cudaFree(ptr));
+    return ZODI_OK;
 }
 
 int64_t zodi_kernel_launch_count(void) { return g_launches.load(); }

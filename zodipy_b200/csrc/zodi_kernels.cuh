@@ -27,10 +27,27 @@ struct LaunchArgs {
     int return_comps;
     int out_f32;
     void* out;            int64_t out_stride;
+    // fused all-gather: store to every peer's map (see zodi_eval_args.peer_out)
+    int n_peers;
+    void* peer_out[ZODI_MAX_PEERS];
+    int64_t peer_offset;  int64_t peer_stride;
 };
 
+// Store one result: row `ci` (component, or 0 for the summed map), column j of this call.
+// With peers: the same element goes to every GPU's full map over NVLink (P2P stores, coalesced
+// across the warp), which is the all-gather of the reference's `np.concatenate` done in the
+// epilogue of the compute kernel.
 template <typename Real>
-__device__ __forceinline__ void store_out(const LaunchArgs& a, int64_t idx, Real v) {
+__device__ __forceinline__ void store_out(const LaunchArgs& a, int ci, int64_t j, Real v) {
+    if (a.n_peers > 0) {
+        const int64_t idx = (int64_t)ci * a.peer_stride + a.peer_offset + j;
+        for (int p = 0; p < a.n_peers; ++p) {
+            if (a.out_f32) reinterpret_cast<float*>(a.peer_out[p])[idx] = (float)v;
+            else reinterpret_cast<double*>(a.peer_out[p])[idx] = (double)v;
+        }
+        return;
+    }
+    const int64_t idx = (int64_t)ci * a.out_stride + j;
     if (a.out_f32) reinterpret_cast<float*>(a.out)[idx] = (float)v;
     else reinterpret_cast<double*>(a.out)[idx] = (double)v;
 }
@@ -80,9 +97,9 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
             const Real v = lane_group_sum<Real, L>(part);
             total += v;  // component order = model order (emission.sum(axis=0), model.py:203)
             if (args.return_comps && active && sub == 0)
-                store_out<Real>(args, (int64_t)ci * args.out_stride + j, v);
+                store_out<Real>(args, ci, j, v);
         });
-    if (!args.return_comps && active && sub == 0) store_out<Real>(args, j, total);
+    if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
 }
 
 // Fused Kelsall-family kernel (zodi_kelsall.cuh): cloud + 3 bands on one shared grid, then ring
@@ -124,9 +141,9 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
             const Real v = lane_group_sum<Real, L>(part);
             total += v;
             if (args.return_comps && active && sub == 0)
-                store_out<Real>(args, (int64_t)ci * args.out_stride + j, v);
+                store_out<Real>(args, ci, j, v);
         });
-    if (!args.return_comps && active && sub == 0) store_out<Real>(args, j, total);
+    if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
 }
 
 // max over observers of r^2 = x^2+y^2+z^2 (for the global early-out flags, quirk Q1).

@@ -95,12 +95,14 @@ class DeviceModel:
         return spec_outside_flags(self.spec, self.max_observer_radius(obs))
 
     def evaluate(self, u, obs, earth=None, *, return_comps: bool = False, precision: str = "fp64",
-                 out=None, out_dtype=None, outside_flags=None):
+                 out=None, out_dtype=None, outside_flags=None, peer_map=None):
         """Emission [MJy/sr] for unit vectors ``u`` (3, N).
 
         ``obs`` / ``earth``: (3,), (3, 1) or (3, N) [AU]; ``earth`` defaults to ``obs``.
         ``outside_flags``: optional (ncomps, 2) uint8 GLOBAL early-out flags (needed when the
         observers of a job are sharded over several calls/GPUs); default: derived from ``obs``.
+        ``peer_map``: a :class:`zodipy_b200.sharding.PeerMap`; the kernel then stores this call's
+        slice directly into every GPU's full map (fused all-gather) and nothing is returned.
         Returns an array like the inputs (NumPy -> NumPy, torch CUDA -> torch CUDA) of shape
         (ncomps, N) if ``return_comps`` else (N,).
         """
@@ -131,7 +133,14 @@ class DeviceModel:
         if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
             raise ValueError("out_dtype must be float64 or float32")
         shape = (self.ncomps, n) if return_comps else (n,)
-        if device_mem:
+        if peer_map is not None:
+            if not device_mem:
+                raise ValueError("peer_map needs device-resident (torch CUDA) inputs")
+            if peer_map.dtype != out_dtype or peer_map.rows != (self.ncomps if return_comps else 1):
+                raise ValueError("peer_map dtype/rows do not match this call")
+            out_ptr, out = None, None
+            stream = torch.cuda.current_stream(u_a.device).cuda_stream
+        elif device_mem:
             tdtype = torch.float64 if out_dtype == np.float64 else torch.float32
             if out is None:
                 out = torch.empty(shape, dtype=tdtype, device=u_a.device)
@@ -148,6 +157,8 @@ class DeviceModel:
             stream = None
         if n == 0:
             return out
+        if peer_map is not None and peer_map.offset + n > peer_map.n_total:
+            raise ValueError("slice does not fit the peer map")
 
         if outside_flags is None:
             if device_mem and n_obs == 1:
@@ -173,6 +184,11 @@ class DeviceModel:
         args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
         args.out, args.out_stride = out_ptr, n
         args.stream = stream
+        if peer_map is not None:
+            args.n_peers = len(peer_map.pointers)
+            for i, ptr in enumerate(peer_map.pointers):
+                args.peer_out[i] = ptr
+            args.peer_offset, args.peer_stride = peer_map.offset, peer_map.n_total
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 

@@ -66,11 +66,118 @@ def allgather_map(local, n: int, group=None):
     if local.shape[-1] != slot:
         send = torch.zeros(lead + (slot,), dtype=local.dtype, device=local.device)
         send[..., : local.shape[-1]] = local
-    gathered = torch.empty((world,) + lead + (slot,), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, send.contiguous(), group=group)
+    # flat 1-D buffers: accepted by both NCCL and gloo (rank r's slot is gathered[r])
+    send = send.contiguous().reshape(-1)
+    on_cuda = send.is_cuda
+    if on_cuda and dist.get_backend(group) == "gloo":
+        send = send.cpu()  # gloo moves host memory (CPU tests / single-GPU multi-process tests)
+    flat = torch.empty(world * send.numel(), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(flat, send, group=group)
+    if on_cuda and not flat.is_cuda:
+        flat = flat.to(local.device)
+    gathered = flat.view((world,) + lead + (slot,))
     if n % world == 0:
         # (world, ..., slot) -> (..., world * slot) without a trim
         return gathered.movedim(0, -2).reshape(lead + (world * slot,))
     parts = [gathered[r, ..., : hi - lo] for r, (lo, hi) in enumerate(bounds)]
     assert parts[rank].shape[-1] == local.shape[-1]
     return torch.cat(parts, dim=-1)
+
+
+def evaluate_sharded(evaluate_fn, max_radius_fn, flags_fn, u_local, obs_local, earth_local, n_total,
+                     *, obs_per_sample: bool, group=None, gather: bool = True, **kwargs):
+    """One rank's part of a sharded evaluation.
+
+    ``u_local`` is this rank's contiguous slice (``split_bounds`` rule) of the (3, n_total)
+    directions; ``obs_local`` / ``earth_local`` are either the rank's slice of per-sample positions
+    (``obs_per_sample``) or the replicated single position.  Steps: local max observer distance ->
+    MAX all-reduce -> identical global early-out flags on every rank (quirk Q1) -> local
+    evaluation -> all-gather of the map.  ``evaluate_fn(u, obs, earth, outside_flags=..., **kwargs)``
+    and ``max_radius_fn(obs)`` / ``flags_fn(r_max)`` are normally bound methods of a
+    :class:`zodipy_b200.engine.DeviceModel`; they are parameters so the plumbing can be tested
+    on CPU with the gloo backend.
+    """
+    r_local = max_radius_fn(obs_local)
+    r_global = global_max_radius(r_local, group) if obs_per_sample else r_local
+    flags = flags_fn(r_global)
+    local = evaluate_fn(u_local, obs_local, earth_local, outside_flags=flags, **kwargs)
+    if not gather:
+        return local
+    return allgather_map(local, n_total, group)
+
+
+class PeerMap:
+    """Full-map output buffers of all ranks, mapped into this process (CUDA IPC over NVLink).
+
+    Every rank allocates one (rows, n_total) buffer with the library (plain ``cudaMalloc`` so
+    that it can be exported), the IPC handles are exchanged once with ``all_gather_object``, and
+    each rank maps every peer's buffer.  ``DeviceModel.evaluate(..., peer_map=pm)`` then makes the
+    compute kernel store this rank's slice into all of them (fused all-gather); ``finish()``
+    is the stream-ordered rendezvous after which ``pm.tensor`` holds the complete map on every
+    rank.  One process per GPU, ranks of one NVSwitch box.
+    """
+
+    def __init__(self, n_total: int, rows: int, dtype, device_index: int, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _cabi
+
+        self._lib = _cabi.load()
+        self.n_total, self.rows = int(n_total), int(rows)
+        self.dtype = np.dtype(dtype)
+        self.device_index = int(device_index)
+        self.group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > _cabi.MAX_PEERS:
+            raise ValueError(f"at most {_cabi.MAX_PEERS} peers")
+        lo, _ = split_bounds(self.n_total, world)[rank]
+        self.offset = lo
+        nbytes = self.rows * self.n_total * self.dtype.itemsize
+        own = C.c_void_p()
+        handle = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES)()
+        _cabi.check(self._lib.zodi_peer_buffer_alloc(self.device_index, nbytes, C.byref(own), handle))
+        self._own = own.value
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.pointers, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.pointers.append(self._own)
+                continue
+            buf = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES).from_buffer_copy(h)
+            ptr = C.c_void_p()
+            _cabi.check(self._lib.zodi_peer_buffer_open(self.device_index, buf, C.byref(ptr)))
+            self.pointers.append(ptr.value)
+            self._opened.append(ptr.value)
+        # torch view of the OWN buffer (no copy)
+        tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
+        shape = (self.rows, self.n_total) if self.rows > 1 else (self.n_total,)
+        iface = {"shape": shape, "typestr": "<f4" if self.dtype == np.float32 else "<f8",
+                 "data": (self._own, False), "version": 2}
+        holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
+        self.tensor = torch.as_tensor(holder, device=torch.device("cuda", self.device_index))
+        assert self.tensor.dtype == tdtype and self.tensor.data_ptr() == self._own
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.tensor.device)
+
+    def finish(self):
+        """Stream-ordered rendezvous: returns once every rank's kernel (and therefore all of its
+        peer stores) has completed.  A 4-byte NCCL all-reduce enqueued behind the kernel."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self._token, group=self.group)
+        return self.tensor
+
+    def close(self):
+        import torch
+
+        torch.cuda.synchronize(self.device_index)
+        for ptr in self._opened:
+            self._lib.zodi_peer_buffer_close(self.device_index, ptr)
+        self._opened = []
+        if self._own:
+            self.tensor = None
+            self._lib.zodi_peer_buffer_free(self.device_index, self._own)
+            self._own = None
