@@ -51,8 +51,9 @@ def _worker(rank, world, port, backend, case_id, per_sample, precision, use_peer
         result = {"gathered": full.cpu().numpy()}
         if use_peer_map:
             pm = sharding.PeerMap(n, dm.ncomps, np.float64, dev_index)
-            r_glob = sharding.global_max_radius(dm.max_observer_radius(obs)) if per_sample else \\
-                dm.max_observer_radius(obs)
+            r_glob = dm.max_observer_radius(obs)
+            if per_sample:
+                r_glob = sharding.global_max_radius(r_glob)
             dm.evaluate(u, obs, earth, return_comps=True, precision=precision,
                         outside_flags=sharding_flags(dm, r_glob), peer_map=pm)
             result["fused"] = pm.finish().cpu().numpy()
