@@ -192,6 +192,9 @@ def cpu_baseline(spec, nside, budget_s=12.0):
 
 
 def run_b200(args):
+    # stdout carries exactly one JSON line: keep NCCL's version banner / debug output off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
 
