@@ -323,6 +323,26 @@ def run_b200(args):
                "api": "Model.evaluate_xyz(numpy pinned host arrays) -> zodi_evaluate(ZODI_MEM_HOST)"}
         # sanity: e2e result equals the device-resident result
         assert np.array_equal(out_np, out_local.cpu().numpy()), "host-path result differs from device path"
+        # additive map entry: directions generated on the device, only the map comes back
+        for _ in range(2):
+            model.evaluate_healpix(args.nside, EARTH, pix_range=(lo, hi), out=out_np, out_dtype=out_dtype)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            model.evaluate_healpix(args.nside, EARTH, pix_range=(lo, hi), out=out_np, out_dtype=out_dtype)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        hp_err = float(np.max(np.abs(out_np - out_local.cpu().numpy()) / np.abs(out_np)))
+        e2e["healpix_entry"] = {
+            "value": units_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_e2e,
+            "h2d_bytes_per_step": 48 * world, "d2h_bytes_per_step": int(npix * out_host.element_size()),
+            "api": "Model.evaluate_healpix(nside, obs) -> zodi_evaluate_healpix(ZODI_MEM_HOST): pixel "
+                   "directions generated in the kernel prologue, map returned to pinned host memory",
+            "max_rel_diff_vs_array_seam": hp_err}
 
     if rank != 0:
         if peer_map is not None:

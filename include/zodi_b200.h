@@ -149,6 +149,22 @@ typedef struct {
     int64_t peer_stride;
 } zodi_eval_args;
 
+/* HEALPix map evaluation with directions generated on the device (no (3, N) upload):
+ * line of sight j of the call is the centre of RING pixel ipix_start + j of resolution nside,
+ * optionally rotated by `rot` (row-major 3x3: pixel frame -> mean ecliptic, i.e. the constant
+ * matrix behind skycoord.transform_to(BarycentricMeanEcliptic), zodipy/model.py:247).
+ * `base.u`/`base.u_stride` are ignored; everything else in `base` keeps its meaning
+ * (base.memory describes obs / earth / out).  Replaces, for map-making callers, healpy.pix2ang +
+ * SkyCoord construction (docs/examples/healpy_map.py:14-18) in front of the same hot path. */
+typedef struct {
+    zodi_eval_args base;
+    int64_t nside;
+    int64_t ipix_start;
+    int32_t nest;      /* 0 = RING (supported); 1 = NESTED (ZODI_ERR_UNSUPPORTED for now) */
+    int32_t has_rot;
+    double rot[9];
+} zodi_healpix_args;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int zodi_abi_version(void);
 const char* zodi_last_error(void);
@@ -165,6 +181,12 @@ int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);
 /* Name of the kernel family zodi_evaluate launches for this model: "zodi_los_kelsall_kernel"
  * (fused Kelsall-family kernel) or "zodi_los_generic_kernel" (any component list). */
 const char* zodi_model_kernel_name(zodi_model_t model);
+
+int zodi_evaluate_healpix(zodi_model_t model, const zodi_healpix_args* args);
+/* Pixel-centre unit vectors (3, n) of RING pixels [ipix_start, ipix_start + n) into device or host
+ * memory (`memory`), rotated by rot if non-NULL: the directions zodi_evaluate_healpix integrates. */
+int zodi_healpix_vectors(int device, int64_t nside, int64_t ipix_start, int64_t n, const double* rot,
+                         double* out, int64_t out_stride, int32_t memory, void* stream);
 
 /* Largest heliocentric observer distance sqrt(x^2+y^2+z^2) over (3, n_obs) observers and the
  * resulting early-out flags; used to form the GLOBAL flags when a job is sharded over GPUs

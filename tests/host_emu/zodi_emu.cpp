@@ -50,7 +50,12 @@ static void run_kelsall(const KelsallModel<Real>& K, const std::vector<Pair<Real
         auto emit = [&](int ci, Real part) { out[ci * n + j] += (double)part; };
         for (int sub = 0; sub < lanes; ++sub) {
 #define ZCALL(RF, SC)                                                                             \
-    integrate_kelsall<Real, RF, SC>(K, tab.data(), nodes.data(), u[j], u[n + j], u[2 * n + j],    \
+    if (K.share13)                                                                                \
+        integrate_kelsall<Real, RF, SC, true>(K, tab.data(), nodes.data(), u[j], u[n + j],         \
+                                    u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo],   \
+                                    earth[je], earth[n_earth + je], mask, sub, lanes, emit);       \
+    else                                                                                          \
+    integrate_kelsall<Real, RF, SC, false>(K, tab.data(), nodes.data(), u[j], u[n + j], u[2 * n + j],    \
                                     obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo], earth[je],     \
                                     earth[n_earth + je], mask, sub, lanes, emit)
             if (K.n_comps == 6) { if (K.scatter) ZCALL(true, true); else ZCALL(true, false); }

@@ -188,3 +188,57 @@ def test_linearity_in_emissivity_full_size():
     scaled = model.evaluate_xyz(u, obs, return_comps=True, out_dtype=np.float32)
     assert torch.allclose(scaled, 3.0 * base, rtol=2e-6, atol=0.0)
     assert bool(torch.isfinite(base).all())
+
+
+def test_healpix_vectors_match_host_pix2vec():
+    from zodipy_b200 import healpix
+
+    for nside in (1, 2, 8, 64, 1024):
+        npix = healpix.nside2npix(nside)
+        rng = (0, npix) if npix <= 49152 else (npix // 2 - 3000, npix // 2 + 3000)
+        got = engine.healpix_vectors(nside, rng)
+        ref = healpix.pix2vec_ring(nside, np.arange(*rng))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=3e-16)
+    # caps of a large map (first / last pixels) and a rotation
+    nside = 2048
+    npix = healpix.nside2npix(nside)
+    for rng in ((0, 5000), (npix - 5000, npix)):
+        np.testing.assert_allclose(engine.healpix_vectors(nside, rng),
+                                   healpix.pix2vec_ring(nside, np.arange(*rng)), rtol=0, atol=3e-16)
+    c, s_ = np.cos(0.4), np.sin(0.4)
+    rot = np.array([[1, 0, 0], [0, c, s_], [0, -s_, c]])
+    np.testing.assert_allclose(engine.healpix_vectors(16, rot=rot),
+                               rot @ healpix.pix2vec_ring(16, np.arange(12 * 256)), rtol=0, atol=4e-16)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_evaluate_healpix_equals_array_seam(precision):
+    """On-device directions give the same map as uploading pix2vec() through the array seam, for
+    host and device outputs, sub-ranges, rotation and return_comps."""
+    import torch
+
+    from zodipy_b200 import healpix
+
+    model = zp.Model(zp.Quantity(25.0, "um"), precision=precision)
+    nside = 64
+    u = healpix.full_sky_vectors(nside)
+    ref = model.evaluate_xyz(u, EARTH_20220114, return_comps=True)
+    tol = 1e-12 if precision == "fp64" else 2e-6
+    got = model.evaluate_healpix(nside, EARTH_20220114, return_comps=True)
+    np.testing.assert_allclose(got, ref, rtol=tol)
+    np.testing.assert_allclose(model.evaluate_healpix(nside, EARTH_20220114), ref.sum(axis=0), rtol=tol)
+    part = model.evaluate_healpix(nside, EARTH_20220114, pix_range=(1000, 20001), out_dtype=np.float32)
+    assert part.dtype == np.float32 and part.shape == (19001,)
+    np.testing.assert_allclose(part, ref.sum(axis=0)[1000:20001], rtol=tol + 1e-6)
+    dev = model.evaluate_healpix(nside, EARTH_20220114, device_out=True)
+    assert dev.is_cuda and torch.allclose(dev.cpu(), torch.from_numpy(ref.sum(axis=0)), rtol=tol, atol=0)
+    c, s_ = np.cos(1.1), np.sin(1.1)
+    rot = np.array([[c, s_, 0], [-s_, c, 0], [0, 0, 1.0]])
+    np.testing.assert_allclose(model.evaluate_healpix(nside, EARTH_20220114, frame_rotation=rot),
+                               model.evaluate_xyz(rot @ u, EARTH_20220114), rtol=tol)
+    # oracle check on a subset
+    sel = np.arange(0, u.shape[1], 97)
+    ref_o = oracle.evaluate(model.spec, u[:, sel], EARTH_20220114, EARTH_20220114)
+    assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
+    with pytest.raises(engine._cabi.ZodiError):
+        model.device_model.evaluate_healpix(0, EARTH_20220114)

@@ -72,6 +72,15 @@ class EvalArgs(C.Structure):
     ]
 
 
+class HealpixArgs(C.Structure):
+    _fields_ = [
+        ("base", EvalArgs),
+        ("nside", C.c_int64), ("ipix_start", C.c_int64),
+        ("nest", C.c_int32), ("has_rot", C.c_int32),
+        ("rot", C.c_double * 9),
+    ]
+
+
 # every symbol include/zodi_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "zodi_abi_version": (C.c_int, []),
@@ -82,6 +91,9 @@ SYMBOLS = {
     "zodi_model_destroy": (C.c_int, [C.c_void_p]),
     "zodi_model_kernel_name": (C.c_char_p, [C.c_void_p]),
     "zodi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
+    "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
+    "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
+                                       C.c_int64, C.c_int32, C.c_void_p]),
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),
     "zodi_flags_from_radius": (C.c_int, [C.c_void_p, C.c_double, c_uint8_p]),

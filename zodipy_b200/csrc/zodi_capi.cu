@@ -121,7 +121,8 @@ int validate_desc(const zodi_model_desc* d) {
 int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     build_dev_model(*d, m->m64);
     narrow_model(m->m64, m->m32);
-    m->kelsall_ok = build_kelsall_model(*d, m->k64);
+    m->kelsall_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes &&
+                    build_kelsall_model(*d, m->k64);
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
     const char* fg = std::getenv("ZODI_FORCE_GENERIC");
     m->force_generic = (fg && fg[0] == '1');
@@ -206,24 +207,30 @@ cudaError_t launch_generic(const DevModel<Real>& M, const LaunchArgs& a, const P
     }
 }
 
-template <typename Real, bool HAS_RF, bool SCATTER, int L>
+template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, int L>
 cudaError_t launch_kelsall_L(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
                              const Pair<Real>* nodes, cudaStream_t stream) {
     const int per_cta = kThreads / L;
     const int64_t grid = (a.n + per_cta - 1) / per_cta;
-    const size_t smem = (size_t)(K.n_temps + K.n_nodes) * sizeof(Pair<Real>);
-    zodi_los_kelsall_kernel<Real, HAS_RF, SCATTER, L><<<(unsigned)grid, kThreads, smem, stream>>>(K, a, tab, nodes);
+    zodi_los_kelsall_kernel<Real, HAS_RF, SCATTER, SHARE13, L>
+        <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13>
+cudaError_t launch_kelsall_RSS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
+                               const Pair<Real>* nodes, cudaStream_t stream) {
+    if (pick_lanes(a.n, K.n_nodes) == 1)
+        return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 1>(K, a, tab, nodes, stream);
+    return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 8>(K, a, tab, nodes, stream);
 }
 
 template <typename Real, bool HAS_RF, bool SCATTER>
 cudaError_t launch_kelsall_RS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
                               const Pair<Real>* nodes, cudaStream_t stream) {
-    const int L = pick_lanes(a.n, K.n_nodes);
-    if (L == 1) return launch_kelsall_L<Real, HAS_RF, SCATTER, 1>(K, a, tab, nodes, stream);
-    if (L <= 4) return launch_kelsall_L<Real, HAS_RF, SCATTER, 4>(K, a, tab, nodes, stream);
-    return launch_kelsall_L<Real, HAS_RF, SCATTER, 16>(K, a, tab, nodes, stream);
+    if (K.share13) return launch_kelsall_RSS<Real, HAS_RF, SCATTER, true>(K, a, tab, nodes, stream);
+    return launch_kelsall_RSS<Real, HAS_RF, SCATTER, false>(K, a, tab, nodes, stream);
 }
 
 template <typename Real>
@@ -272,7 +279,7 @@ double max_r_host(const double* obs, int64_t n_obs, int64_t stride) {
     return std::sqrt(m);
 }
 
-int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
+int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = true) {
     if (!m) return fail(ZODI_ERR_INVALID, "model handle is NULL");
     if (!a) return fail(ZODI_ERR_INVALID, "eval args are NULL");
     if (a->n < 0) return fail(ZODI_ERR_INVALID, "n=%lld is negative", (long long)a->n);
@@ -287,7 +294,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
         if (a->peer_offset < 0 || (a->return_comps && a->peer_stride < a->peer_offset + a->n))
             return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
     }
-    if (!a->u || !a->obs || !a->earth || (!a->out && a->n_peers == 0))
+    if ((need_u && !a->u) || !a->obs || !a->earth || (!a->out && a->n_peers == 0))
         return fail(ZODI_ERR_INVALID, "u/obs/earth/out must be non-NULL");
     if (a->n_obs != 1 && a->n_obs != a->n)
         return fail(ZODI_ERR_INVALID, "n_obs=%lld must be 1 or n=%lld", (long long)a->n_obs,
@@ -295,7 +302,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
     if (a->n_earth != 1 && a->n_earth != a->n)
         return fail(ZODI_ERR_INVALID, "n_earth=%lld must be 1 or n=%lld", (long long)a->n_earth,
                     (long long)a->n);
-    if (a->u_stride < a->n || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
+    if ((need_u && a->u_stride < a->n) || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
         return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
     if (a->return_comps && a->n_peers == 0 && a->out_stride < a->n)
         return fail(ZODI_ERR_INVALID, "out_stride=%lld < n", (long long)a->out_stride);
@@ -306,6 +313,16 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a) {
     if (a->memory != ZODI_MEM_HOST && a->memory != ZODI_MEM_DEVICE)
         return fail(ZODI_ERR_INVALID, "unknown memory kind %d", a->memory);
     return ZODI_OK;
+}
+
+void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
+    la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0;
+    for (int i = 0; i < 9; ++i) la.hp_rot[i] = 0.0;
+    if (!hp) return;
+    la.hp_nside = hp->nside;
+    la.hp_start = hp->ipix_start + offset;
+    la.hp_rotate = hp->has_rot != 0;
+    for (int i = 0; i < 9; ++i) la.hp_rot[i] = hp->rot[i];
 }
 
 // ---- host-memory path: chunked, 3-deep pipeline H2D | kernel | D2H on private streams ------
@@ -323,7 +340,7 @@ int ensure_workspace(zodi_model_s* m, int64_t chunk) {
     return ZODI_OK;
 }
 
-int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask) {
+int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const zodi_healpix_args* hp) {
     std::lock_guard<std::mutex> lock(m->ws_mutex);
     const int64_t n = a->n;
     int64_t chunk = 1 << 20;
@@ -347,8 +364,9 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask) {
         double* d_obs = s.d_in + 3 * m->ws_chunk;
         double* d_earth = s.d_in + 6 * m->ws_chunk;
         const size_t pitch = (size_t)m->ws_chunk * sizeof(double);
-        CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
-                                   (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
+        if (!hp)
+            CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
+                                       (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
         CU_CHECK(cudaMemcpy2DAsync(d_obs, pitch, a->obs + (obs_ps ? done : 0),
                                    (size_t)a->obs_stride * sizeof(double),
                                    (size_t)(obs_ps ? cn : 1) * sizeof(double), 3,
@@ -368,6 +386,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask) {
         la.out_f32 = a->out_dtype == ZODI_OUT_F32;
         la.out = s.d_out; la.out_stride = m->ws_chunk;
         la.n_peers = 0; la.peer_offset = 0; la.peer_stride = 0;
+        set_healpix(la, hp, done);
         if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
         CU_CHECK(launch_eval(m, la, a->precision, s.stream));
         CU_CHECK(cudaEventRecord(s.k1, s.stream));
@@ -476,8 +495,8 @@ int zodi_max_observer_radius(zodi_model_t m, const double* obs, int64_t n_obs, i
     return max_r_device(m, obs, n_obs, obs_stride, (cudaStream_t)stream, r_max);
 }
 
-int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
-    int rc = check_args(m, a);
+static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_healpix_args* hp) {
+    int rc = check_args(m, a, hp == nullptr);
     if (rc) return rc;
     if (a->n == 0) return ZODI_OK;
     DeviceGuard guard(m->device);
@@ -498,7 +517,7 @@ int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
     }
     const uint32_t mask = flags_to_mask(flags, m->desc.n_comps);
 
-    if (a->memory == ZODI_MEM_HOST) return evaluate_host(m, a, mask);
+    if (a->memory == ZODI_MEM_HOST) return evaluate_host(m, a, mask, hp);
 
     LaunchArgs la;
     la.n = a->n;
@@ -512,7 +531,63 @@ int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) {
     la.out = a->out; la.out_stride = a->out_stride;
     la.n_peers = a->n_peers; la.peer_offset = a->peer_offset; la.peer_stride = a->peer_stride;
     for (int p = 0; p < ZODI_MAX_PEERS; ++p) la.peer_out[p] = p < a->n_peers ? a->peer_out[p] : nullptr;
+    set_healpix(la, hp, 0);
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
+    return ZODI_OK;
+}
+
+int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) { return evaluate_impl(m, a, nullptr); }
+
+static int check_healpix(int64_t nside, int64_t ipix_start, int64_t n, int nest) {
+    if (nest) return fail(ZODI_ERR_UNSUPPORTED, "NESTED pixel ordering is not implemented yet");
+    if (nside < 1 || nside > (1ll << 29)) return fail(ZODI_ERR_INVALID, "nside=%lld out of range", (long long)nside);
+    const int64_t npix = 12 * nside * nside;
+    if (ipix_start < 0 || n < 0 || ipix_start + n > npix)
+        return fail(ZODI_ERR_INVALID, "pixel range [%lld, %lld) outside [0, %lld)", (long long)ipix_start,
+                    (long long)(ipix_start + n), (long long)npix);
+    return ZODI_OK;
+}
+
+int zodi_evaluate_healpix(zodi_model_t m, const zodi_healpix_args* hp) {
+    if (!hp) return fail(ZODI_ERR_INVALID, "healpix args are NULL");
+    int rc = check_healpix(hp->nside, hp->ipix_start, hp->base.n, hp->nest);
+    if (rc) return rc;
+    if (hp->base.n_obs != 1 && hp->base.n_obs != hp->base.n)
+        return fail(ZODI_ERR_INVALID, "n_obs must be 1 or n");
+    return evaluate_impl(m, &hp->base, hp);
+}
+
+int zodi_healpix_vectors(int device, int64_t nside, int64_t ipix_start, int64_t n, const double* rot,
+                         double* out, int64_t out_stride, int32_t memory, void* stream) {
+    int rc = check_healpix(nside, ipix_start, n, 0);
+    if (rc) return rc;
+    if (!out || out_stride < n) return fail(ZODI_ERR_INVALID, "bad output buffer");
+    if (n == 0) return ZODI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    LaunchArgs la;
+    std::memset(&la, 0, sizeof(la));
+    la.n = n;
+    zodi_healpix_args hp;
+    std::memset(&hp, 0, sizeof(hp));
+    hp.nside = nside; hp.ipix_start = ipix_start; hp.has_rot = rot != nullptr;
+    if (rot) std::memcpy(hp.rot, rot, sizeof(hp.rot));
+    set_healpix(la, &hp, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_out = out;
+    if (memory == ZODI_MEM_HOST) {
+        st = nullptr;
+        CU_CHECK(cudaMalloc((void**)&d_out, (size_t)3 * n * sizeof(double)));
+    }
+    const int64_t ld = memory == ZODI_MEM_HOST ? n : out_stride;
+    zodi_healpix_vectors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(la, d_out, ld);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && memory == ZODI_MEM_HOST)
+        e = cudaMemcpy2D(out, (size_t)out_stride * sizeof(double), d_out, (size_t)n * sizeof(double),
+                         (size_t)n * sizeof(double), 3, cudaMemcpyDeviceToHost);
+    if (memory == ZODI_MEM_HOST) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ZODI_ERR_CUDA, "healpix vectors failed: %s", cudaGetErrorString(e));
     return ZODI_OK;
 }
 

@@ -132,7 +132,7 @@ ZODI_HD Real band_radial(Real Rh2, Real by) {
     return M::one_minus_exp2_neg(y5 * y5);
 }
 
-template <typename Real, bool HAS_RF, bool SCATTER, typename Emit>
+template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, typename Emit>
 ZODI_HD void integrate_kelsall(const KelsallModel<Real>& K, const Pair<Real>* tab,
                                const Pair<Real>* nodes, double dux, double duy, double duz,
                                double dox, double doy, double doz, double dex, double dey,
@@ -157,7 +157,7 @@ ZODI_HD void integrate_kelsall(const KelsallModel<Real>& K, const Pair<Real>* ta
             const Real rinv = M::rsqrt_(s.Rh2);
             const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
             const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
-            const Real rad3 = K.share13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
+            const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
             const Real n1 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]) * (rinv * rad1);
             const Real n2 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]) * (rinv * rad2);
             const Real n3 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]) * (rinv * rad3);

@@ -31,7 +31,28 @@ struct LaunchArgs {
     int n_peers;
     void* peer_out[ZODI_MAX_PEERS];
     int64_t peer_offset;  int64_t peer_stride;
+    // on-device directions: HEALPix RING pixel hp_start + j (u is ignored when hp_nside > 0)
+    int64_t hp_nside;     int64_t hp_start;
+    int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel vector
 };
+
+// Direction of line of sight j: loaded (reference array seam) or generated from the pixel index.
+__device__ __forceinline__ void load_direction(const LaunchArgs& a, int64_t jj, double& ux, double& uy,
+                                               double& uz) {
+    if (a.hp_nside > 0) {
+        double x, y, z;
+        healpix_ring_pix2vec(a.hp_nside, a.hp_start + jj, x, y, z);
+        if (a.hp_rotate) {
+            ux = a.hp_rot[0] * x + a.hp_rot[1] * y + a.hp_rot[2] * z;
+            uy = a.hp_rot[3] * x + a.hp_rot[4] * y + a.hp_rot[5] * z;
+            uz = a.hp_rot[6] * x + a.hp_rot[7] * y + a.hp_rot[8] * z;
+        } else {
+            ux = x; uy = y; uz = z;
+        }
+    } else {
+        ux = a.u[jj]; uy = a.u[a.u_stride + jj]; uz = a.u[2 * a.u_stride + jj];
+    }
+}
 
 // Store one result: row `ci` (component, or 0 for the summed map), column j of this call.
 // With peers: the same element goes to every GPU's full map over NVLink (P2P stores, coalesced
@@ -79,7 +100,8 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
     const bool active = j < args.n;
     const int64_t jj = active ? j : args.n - 1;  // keep whole warps converged for the shuffles
 
-    const double ux = args.u[jj], uy = args.u[args.u_stride + jj], uz = args.u[2 * args.u_stride + jj];
+    double ux, uy, uz;
+    load_direction(args, jj, ux, uy, uz);
     const int64_t jo = args.obs_per_sample ? jj : 0;
     const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
                  oz = args.obs[2 * args.obs_stride + jo];
@@ -104,15 +126,21 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
 
 // Fused Kelsall-family kernel (zodi_kelsall.cuh): cloud + 3 bands on one shared grid, then ring
 // and feature.  Same thread mapping and staging as the generic kernel.
-template <typename Real, bool HAS_RF, bool SCATTER, int L>
+// Static shared capacity of the fused kernel (the reference uses 100 knots and 50 nodes); larger
+// tables / rules take the generic kernel, whose staging area is sized dynamically.
+constexpr int kFastMaxTemps = 128;
+constexpr int kFastMaxNodes = 128;
+
+template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, int L>
 __global__ void __launch_bounds__(kThreads)
 zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
                         const __grid_constant__ LaunchArgs args,
                         const Pair<Real>* __restrict__ g_table,
                         const Pair<Real>* __restrict__ g_nodes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Pair<Real>* s_table = reinterpret_cast<Pair<Real>*>(smem_raw);
-    Pair<Real>* s_nodes = s_table + model.n_temps;
+    // static arrays: their shared-window addresses are compile-time constants, which keeps the
+    // per-node address arithmetic out of the (issue-bound) hot loop
+    __shared__ Pair<Real> s_table[kFastMaxTemps];
+    __shared__ Pair<Real> s_nodes[kFastMaxNodes];
     for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
     for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
     __syncthreads();
@@ -123,7 +151,8 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
     const bool active = j < args.n;
     const int64_t jj = active ? j : args.n - 1;
 
-    const double ux = args.u[jj], uy = args.u[args.u_stride + jj], uz = args.u[2 * args.u_stride + jj];
+    double ux, uy, uz;
+    load_direction(args, jj, ux, uy, uz);
     const int64_t jo = args.obs_per_sample ? jj : 0;
     const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
                  oz = args.obs[2 * args.obs_stride + jo];
@@ -135,7 +164,7 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
     }
 
     Real total = Real(0);
-    integrate_kelsall<Real, HAS_RF, SCATTER>(
+    integrate_kelsall<Real, HAS_RF, SCATTER, SHARE13>(
         model, s_table, s_nodes, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, sub, L,
         [&](int ci, Real part) {
             const Real v = lane_group_sum<Real, L>(part);
@@ -144,6 +173,16 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
                 store_out<Real>(args, ci, j, v);
         });
     if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
+}
+
+// Pixel-centre unit vectors only (same device routine the integrator uses in its prologue).
+__global__ void zodi_healpix_vectors_kernel(const __grid_constant__ LaunchArgs args, double* __restrict__ out,
+                                            int64_t out_stride) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= args.n) return;
+    double ux, uy, uz;
+    load_direction(args, j, ux, uy, uz);
+    out[j] = ux; out[out_stride + j] = uy; out[2 * out_stride + j] = uz;
 }
 
 // max over observers of r^2 = x^2+y^2+z^2 (for the global early-out flags, quirk Q1).

@@ -192,6 +192,89 @@ class DeviceModel:
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 
+    def evaluate_healpix(self, nside: int, obs, earth=None, *, pix_range=None, rot=None,
+                         return_comps: bool = False, precision: str = "fp64", out=None,
+                         out_dtype=None, device_out: bool = False, peer_map=None):
+        """Emission for HEALPix RING pixels with the directions generated ON THE DEVICE.
+
+        Line of sight j is the centre of pixel ``pix_range[0] + j`` (default: the whole map),
+        rotated by the optional 3x3 ``rot`` (pixel frame -> mean ecliptic).  ``obs`` / ``earth``
+        are single positions (3,) [AU] (instantaneous map).  Nothing but these few numbers is
+        uploaded; the result is returned as a NumPy array (host; D2H pipelined inside the
+        library) or, with ``device_out=True`` / ``peer_map``, left on the GPU as a torch tensor.
+        """
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        nside = int(nside)
+        npix = 12 * nside * nside
+        lo, hi = (0, npix) if pix_range is None else (int(pix_range[0]), int(pix_range[1]))
+        if not 0 <= lo <= hi <= npix:
+            raise ValueError("pix_range outside the map")
+        n = hi - lo
+        obs_h = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(3, 1))
+        earth_h = obs_h if earth is None else np.ascontiguousarray(
+            np.asarray(earth, dtype=np.float64).reshape(3, 1))
+        out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        shape = (self.ncomps, n) if return_comps else (n,)
+        on_device = device_out or peer_map is not None
+        keep = []
+        if on_device:
+            import torch
+
+            dev = torch.device("cuda", self.device)
+            obs_d, earth_d = torch.as_tensor(obs_h, device=dev), torch.as_tensor(earth_h, device=dev)
+            keep += [obs_d, earth_d]
+            obs_ptr, earth_ptr = obs_d.data_ptr(), earth_d.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if peer_map is None:
+                tdtype = torch.float64 if out_dtype == np.float64 else torch.float32
+                if out is None:
+                    out = torch.empty(shape, dtype=tdtype, device=dev)
+                elif tuple(out.shape) != shape or out.dtype != tdtype or not out.is_contiguous():
+                    raise ValueError("out has wrong shape/dtype or is not contiguous")
+                out_ptr = out.data_ptr()
+            else:
+                if peer_map.dtype != out_dtype or peer_map.rows != (self.ncomps if return_comps else 1):
+                    raise ValueError("peer_map dtype/rows do not match this call")
+                out_ptr, out = None, None
+        else:
+            obs_ptr, earth_ptr, stream = obs_h.ctypes.data, earth_h.ctypes.data, None
+            if out is None:
+                out = np.empty(shape, dtype=out_dtype)
+            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            out_ptr = out.ctypes.data
+        if n == 0:
+            return out
+        flags = spec_outside_flags(self.spec, float(np.sqrt((obs_h ** 2).sum())))
+        h = _cabi.HealpixArgs()
+        a = h.base
+        a.n = n
+        a.u, a.u_stride = None, 0
+        a.obs, a.n_obs, a.obs_stride = obs_ptr, 1, 1
+        a.earth, a.n_earth, a.earth_stride = earth_ptr, 1, 1
+        a.outside_flags = flags.ctypes.data_as(_cabi.c_uint8_p)
+        a.return_comps = int(bool(return_comps))
+        a.precision = _PRECISIONS[precision]
+        a.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
+        a.memory = _cabi.MEM_DEVICE if on_device else _cabi.MEM_HOST
+        a.out, a.out_stride = out_ptr, n
+        a.stream = stream
+        if peer_map is not None:
+            a.n_peers = len(peer_map.pointers)
+            for i, ptr in enumerate(peer_map.pointers):
+                a.peer_out[i] = ptr
+            a.peer_offset, a.peer_stride = peer_map.offset, peer_map.n_total
+        h.nside, h.ipix_start, h.nest = nside, lo, 0
+        if rot is not None:
+            r = np.asarray(rot, dtype=np.float64).reshape(9)
+            h.has_rot = 1
+            for i in range(9):
+                h.rot[i] = float(r[i])
+        _cabi.check(self._lib.zodi_evaluate_healpix(self._handle, C.byref(h)))
+        del keep
+        return out
+
     @property
     def kernel_name(self) -> str:
         return self._lib.zodi_model_kernel_name(self._handle).decode()
@@ -202,6 +285,20 @@ class DeviceModel:
 
 def kernel_launch_count() -> int:
     return int(_cabi.load().zodi_kernel_launch_count())
+
+
+def healpix_vectors(nside: int, pix_range=None, rot=None, device: int = 0) -> np.ndarray:
+    """(3, n) RING pixel-centre unit vectors computed by the device routine (host array)."""
+    nside = int(nside)
+    lo, hi = (0, 12 * nside * nside) if pix_range is None else (int(pix_range[0]), int(pix_range[1]))
+    out = np.empty((3, hi - lo), dtype=np.float64)
+    rot_p = None
+    if rot is not None:
+        rot_a = np.ascontiguousarray(np.asarray(rot, dtype=np.float64).reshape(9))
+        rot_p = _cabi.as_double_p(rot_a)
+    _cabi.check(_cabi.load().zodi_healpix_vectors(int(device), nside, lo, hi - lo, rot_p, out.ctypes.data,
+                                                  max(hi - lo, 1), _cabi.MEM_HOST, None))
+    return out
 
 
 def peak_probe(kind: str, device: int = 0) -> float:
