@@ -240,5 +240,6 @@ def test_evaluate_healpix_equals_array_seam(precision):
     sel = np.arange(0, u.shape[1], 97)
     ref_o = oracle.evaluate(model.spec, u[:, sel], EARTH_20220114, EARTH_20220114)
     assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
-    with pytest.raises(engine._cabi.ZodiError):
-        model.device_model.evaluate_healpix(0, EARTH_20220114)
+    with pytest.raises(ValueError):
+        model.evaluate_healpix(4, EARTH_20220114, pix_range=(0, 12 * 16 + 1))
+    assert model.evaluate_healpix(4, EARTH_20220114, pix_range=(7, 7)).shape == (0,)
