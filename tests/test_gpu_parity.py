@@ -13,19 +13,22 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp64": (TOL_FP64, COMP_FLOOR_FP64), "fp32": (TOL_FP32, COMP_FLOOR_FP32)}
 
 
-def device_model(spec, generic=False):
-    """generic=True forces the generic kernel for models the fused Kelsall kernel would take."""
+def device_model(spec, generic=False, no_x2=False):
+    """generic=True forces the generic kernel for models the fused Kelsall kernel would take;
+    no_x2=True the scalar fused kernel where the packed (2 lines of sight per thread) one would run."""
     import os
 
-    old = os.environ.get("ZODI_FORCE_GENERIC")
-    os.environ["ZODI_FORCE_GENERIC"] = "1" if generic else "0"
+    knobs = {"ZODI_FORCE_GENERIC": "1" if generic else "0", "ZODI_NO_X2": "1" if no_x2 else "0"}
+    old = {k: os.environ.get(k) for k in knobs}
+    os.environ.update(knobs)
     try:
         return engine.DeviceModel(spec, device=0)
     finally:
-        if old is None:
-            os.environ.pop("ZODI_FORCE_GENERIC", None)
-        else:
-            os.environ["ZODI_FORCE_GENERIC"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def test_kernel_selection():
@@ -243,3 +246,28 @@ def test_evaluate_healpix_equals_array_seam(precision):
     with pytest.raises(ValueError):
         model.evaluate_healpix(4, EARTH_20220114, pix_range=(0, 12 * 16 + 1))
     assert model.evaluate_healpix(4, EARTH_20220114, pix_range=(7, 7)).shape == (0,)
+
+
+@pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um"),
+                                         ("planck13", 545.0, "GHz")])
+def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
+    """The packed-fp32 kernel (FFMA2, two lines of sight per thread) performs the same operations
+    as the scalar fused kernel: results must be bit-identical (incl. ragged tails, per-sample
+    observers), and within tolerance of the oracle."""
+    model = zp.Model(zp.Quantity(x, unit), name=name, precision="fp32")
+    n = 148 * 2048 * 2 + 777  # large enough for the packed kernel, ragged tail
+    u = fibonacci_sphere(n)
+    rng = np.random.default_rng(5)
+    obs = EARTH_20220114 * (1.0 + 0.02 * rng.standard_normal((1, n)))
+    packed, scalar = device_model(model.spec), device_model(model.spec, no_x2=True)
+    for kwargs in ({"return_comps": True}, {"return_comps": False}):
+        a = packed.evaluate(u, EARTH_20220114, precision="fp32", **kwargs)
+        b = scalar.evaluate(u, EARTH_20220114, precision="fp32", **kwargs)
+        np.testing.assert_array_equal(a, b)
+    a = packed.evaluate(u, obs, EARTH_20220114, precision="fp32", return_comps=True)
+    b = scalar.evaluate(u, obs, EARTH_20220114, precision="fp32", return_comps=True)
+    np.testing.assert_array_equal(a, b)
+    sel = rng.choice(n, 2000, replace=False)
+    ref = oracle.evaluate(model.spec, u[:, sel], obs[:, sel], EARTH_20220114)
+    assert max_rel_total(a[:, sel], ref) <= TOL_FP32
+    assert max_rel_comps(a[:, sel], ref, floor=COMP_FLOOR_FP32) <= TOL_FP32

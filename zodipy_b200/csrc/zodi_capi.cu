@@ -74,6 +74,7 @@ struct zodi_model_s {
     KelsallModel<double> k64;
     KelsallModel<float> k32;
     int force_generic = 0;    // testing knob (ZODI_FORCE_GENERIC=1): always use the generic kernel
+    int no_x2 = 0;            // testing knob (ZODI_NO_X2=1): scalar fused kernel instead of packed
     Pair<double>* d_table64 = nullptr;
     Pair<double>* d_nodes64 = nullptr;
     Pair<float>* d_table32 = nullptr;
@@ -126,6 +127,8 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
     const char* fg = std::getenv("ZODI_FORCE_GENERIC");
     m->force_generic = (fg && fg[0] == '1');
+    const char* nx = std::getenv("ZODI_NO_X2");
+    m->no_x2 = (nx && nx[0] == '1');
 
     // ---- table as (B_i, B_{i+1}-B_i) pairs, nodes as (x_k, w_k) pairs ----
     std::vector<Pair<double>> t64, n64;
@@ -244,9 +247,28 @@ cudaError_t launch_kelsall(const KelsallModel<Real>& K, const LaunchArgs& a, con
     return launch_kelsall_RS<Real, false, false>(K, a, tab, nodes, stream);
 }
 
+template <bool HAS_RF, bool SHARE13>
+cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
+                              const Pair<float>* nodes, cudaStream_t stream) {
+    const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
+    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13><<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     if (m->kelsall_ok && !m->force_generic) {
+        // packed-fp32 kernel: fp32, thermal-only, enough lines of sight for thread-per-pair mapping
+        if (precision == ZODI_FP32 && !m->k32.scatter && !m->no_x2 &&
+            pick_lanes(a.n / 2, m->k32.n_nodes) == 1) {
+            const KelsallModel<float>& K = m->k32;
+            if (K.n_comps == 6)
+                return K.share13 ? launch_kelsall_x2<true, true>(K, a, m->d_table32, m->d_nodes32, stream)
+                                 : launch_kelsall_x2<true, false>(K, a, m->d_table32, m->d_nodes32, stream);
+            return K.share13 ? launch_kelsall_x2<false, true>(K, a, m->d_table32, m->d_nodes32, stream)
+                             : launch_kelsall_x2<false, false>(K, a, m->d_table32, m->d_nodes32, stream);
+        }
         if (precision == ZODI_FP32) return launch_kelsall<float>(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall<double>(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }

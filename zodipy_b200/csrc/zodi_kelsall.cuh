@@ -120,7 +120,7 @@ ZODI_HD Real band_vertical(Real xh, Real yh, Real zh, Real rinv, Real bx, Real b
     using M = Math<Real>;
     const Real sz = M::fma_(xh, bx, M::fma_(yh, by, zh * bz)) * rinv;  // sign irrelevant (even powers)
     const Real s2 = sz * sz, s4 = s2 * s2;
-    return M::exp2_(-(s4 * s2)) * M::fma_(s4, c3, Real(1));
+    return M::exp2_neg_(s4 * s2) * M::fma_(s4, c3, Real(1));
 }
 
 // 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20)
@@ -132,103 +132,138 @@ ZODI_HD Real band_radial(Real Rh2, Real by) {
     return M::one_minus_exp2_neg(y5 * y5);
 }
 
+// Per-line-of-sight quantities shared by the component groups (prologue in double).
+template <typename Real>
+struct LosGeometry {
+    double r_obs2, bq;       // observer distance^2 and b/2 of the ray/sphere quadratic
+    Real ux, uy, uz, ox, oy, oz;
+};
+
+template <typename Real>
+ZODI_HD LosGeometry<Real> los_geometry(double dux, double duy, double duz, double dox, double doy,
+                                       double doz) {
+    LosGeometry<Real> g;
+    g.r_obs2 = dox * dox + doy * doy + doz * doz;
+    g.bq = ray_bq(dux, duy, duz, dox, doy);
+    g.ux = Real(dux); g.uy = Real(duy); g.uz = Real(duz);
+    g.ox = Real(dox); g.oy = Real(doy); g.oz = Real(doz);
+    return g;
+}
+
+// Half-range and mid-point of the quadrature interval between two cutoff spheres.
+template <typename Real>
+ZODI_HD void los_interval(const LosGeometry<Real>& g, double cut_in, double cut_out, bool out_in,
+                          bool out_out, Real& h, Real& mid) {
+    const double start = sphere_distance(g.bq, g.r_obs2, cut_in, out_in);
+    const double stop = sphere_distance(g.bq, g.r_obs2, cut_out, out_out);
+    h = Real(0.5 * (stop - start));    // brightness.py:41
+    mid = Real(0.5 * (stop + start));
+}
+
+// ---------------- group A: cloud + band1..3 on one grid ---------------------------------------
+template <typename Real, bool SCATTER, bool SHARE13, typename Emit>
+ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab, const Pair<Real>* nodes,
+                             const LosGeometry<Real>& G, uint32_t outside_mask, int sub, int L, Emit emit) {
+    using M = Math<Real>;
+    Real h, mid;
+    los_interval<Real>(G, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, h, mid);
+    Real aB0 = 0, aB1 = 0, aB2 = 0, aB3 = 0, aS0 = 0, aS1 = 0, aS2 = 0, aS3 = 0;
+    for (int k = sub; k < K.n_nodes; k += L) {
+        const Pair<Real> nw = nodes[k];
+        const NodeSource<Real> s = node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), G.ux, G.uy,
+                                                              G.uz, G.ox, G.oy, G.oz);
+        // bands: centred on the Sun -> share R
+        const Real rinv = M::rsqrt_(s.Rh2);
+        const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
+        const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
+        const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
+        const Real n1 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]) * (rinv * rad1);
+        const Real n2 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]) * (rinv * rad2);
+        const Real n3 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]) * (rinv * rad3);
+        // cloud
+        const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
+        const Real Rc2 = M::fma_(xc, xc, M::fma_(yc, yc, zc * zc));
+        const Real zeta = M::abs_(M::fma_(xc, K.cnx, M::fma_(yc, K.cny, zc * K.cnz))) * M::rsqrt_(Rc2);
+        const Real g = (zeta < K.c_mu) ? zeta * zeta * K.c_inv2mu : zeta - K.c_halfmu;
+        const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
+        const Real n0 = M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
+
+        const Real wB = nw.b * s.B;
+        aB0 = M::fma_(wB, n0, aB0); aB1 = M::fma_(wB, n1, aB1);
+        aB2 = M::fma_(wB, n2, aB2); aB3 = M::fma_(wB, n3, aB3);
+        if (SCATTER) {
+            const Real wF = nw.b * s.F;
+            aS0 = M::fma_(wF, n0, aS0); aS1 = M::fma_(wF, n1, aS1);
+            aS2 = M::fma_(wF, n2, aS2); aS3 = M::fma_(wF, n3, aS3);
+        }
+    }
+    emit(0, h * M::fma_(K.aB[0], aB0, K.aS[0] * aS0));
+    emit(1, h * M::fma_(K.aB[1], aB1, K.aS[1] * aS1));
+    emit(2, h * M::fma_(K.aB[2], aB2, K.aS[2] * aS2));
+    emit(3, h * M::fma_(K.aB[3], aB3, K.aS[3] * aS3));
+}
+
+// ---------------- ring (own grid) -------------------------------------------------------------
+template <typename Real, bool SCATTER>
+ZODI_HD Real kelsall_ring(const KelsallModel<Real>& K, const Pair<Real>* tab, const Pair<Real>* nodes,
+                          const LosGeometry<Real>& G, uint32_t outside_mask, int sub, int L) {
+    using M = Math<Real>;
+    Real h, mid;
+    los_interval<Real>(G, K.cutR_in, K.cutR_out, (outside_mask >> 8) & 1u, (outside_mask >> 9) & 1u, h, mid);
+    Real aB = 0, aS = 0;
+    for (int k = sub; k < K.n_nodes; k += L) {
+        const Pair<Real> nw = nodes[k];
+        const NodeSource<Real> s = node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), G.ux, G.uy,
+                                                              G.uz, G.ox, G.oy, G.oz);
+        const Real d = M::sqrt_(s.Rh2) - K.r_R;
+        const Real Zc = M::fma_(s.xh, K.rnx, M::fma_(s.yh, K.rny, s.zh * K.rnz));
+        const Real n = M::exp2_neg_(-M::fma_(d * d, K.r_c2, M::abs_(Zc) * K.r_c3));
+        aB = M::fma_(nw.b * s.B, n, aB);
+        if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
+    }
+    return h * M::fma_(K.aB[4], aB, K.aS[4] * aS);
+}
+
+// ---------------- feature (own grid) ----------------------------------------------------------
+template <typename Real, bool SCATTER>
+ZODI_HD Real kelsall_feature(const KelsallModel<Real>& K, const Pair<Real>* tab, const Pair<Real>* nodes,
+                             const LosGeometry<Real>& G, double dex, double dey, uint32_t outside_mask,
+                             int sub, int L) {
+    using M = Math<Real>;
+    Real h, mid;
+    los_interval<Real>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, h, mid);
+    // rotate by -(theta_earth + theta_0): then atan2 gives the wrapped longitude offset directly
+    // (number_density.py:163-170; [-pi,pi) vs (-pi,pi] only differs at |delta| = pi where the
+    // squared offset is identical)
+    const double th = atan2(dey, dex) + (double)K.f_theta0;
+    const Real cr = Real(cos(th)), sr = Real(sin(th));
+    Real aB = 0, aS = 0;
+    for (int k = sub; k < K.n_nodes; k += L) {
+        const Pair<Real> nw = nodes[k];
+        const NodeSource<Real> s = node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), G.ux, G.uy,
+                                                              G.uz, G.ox, G.oy, G.oz);
+        const Real d = M::sqrt_(s.Rh2) - K.f_R;
+        const Real Zc = M::fma_(s.xh, K.fnx, M::fma_(s.yh, K.fny, s.zh * K.fnz));
+        const Real xr = M::fma_(s.xh, cr, s.yh * sr), yr = M::fma_(s.yh, cr, -(s.xh * sr));
+        const Real dth = M::atan2_(yr, xr);
+        const Real e = M::fma_(d * d, K.f_c2, M::fma_(M::abs_(Zc), K.f_c3, dth * dth * K.f_c5));
+        const Real n = M::exp2_neg_(-e);
+        aB = M::fma_(nw.b * s.B, n, aB);
+        if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
+    }
+    return h * M::fma_(K.aB[5], aB, K.aS[5] * aS);
+}
+
 template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, typename Emit>
 ZODI_HD void integrate_kelsall(const KelsallModel<Real>& K, const Pair<Real>* tab,
                                const Pair<Real>* nodes, double dux, double duy, double duz,
                                double dox, double doy, double doz, double dex, double dey,
                                uint32_t outside_mask, int sub, int L, Emit emit) {
-    using M = Math<Real>;
-    const double r_obs2 = dox * dox + doy * doy + doz * doz;
-    const double bq = ray_bq(dux, duy, duz, dox, doy);
-    const Real ux = Real(dux), uy = Real(duy), uz = Real(duz);
-    const Real ox = Real(dox), oy = Real(doy), oz = Real(doz);
-
-    // ---------------- group A: cloud + band1..3 on one grid --------------------------------
-    {
-        const double start = sphere_distance(bq, r_obs2, K.cutA_in, outside_mask & 1u);
-        const double stop = sphere_distance(bq, r_obs2, K.cutA_out, (outside_mask >> 1) & 1u);
-        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
-        Real aB0 = 0, aB1 = 0, aB2 = 0, aB3 = 0, aS0 = 0, aS1 = 0, aS2 = 0, aS3 = 0;
-        for (int k = sub; k < K.n_nodes; k += L) {
-            const Pair<Real> nw = nodes[k];
-            const NodeSource<Real> s =
-                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
-            // bands: centred on the Sun -> share R
-            const Real rinv = M::rsqrt_(s.Rh2);
-            const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
-            const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
-            const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
-            const Real n1 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]) * (rinv * rad1);
-            const Real n2 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]) * (rinv * rad2);
-            const Real n3 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]) * (rinv * rad3);
-            // cloud
-            const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
-            const Real Rc2 = M::fma_(xc, xc, M::fma_(yc, yc, zc * zc));
-            const Real zeta = M::abs_(M::fma_(xc, K.cnx, M::fma_(yc, K.cny, zc * K.cnz))) * M::rsqrt_(Rc2);
-            const Real g = (zeta < K.c_mu) ? zeta * zeta * K.c_inv2mu : zeta - K.c_halfmu;
-            const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
-            const Real n0 = M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
-
-            const Real wB = nw.b * s.B;
-            aB0 = M::fma_(wB, n0, aB0); aB1 = M::fma_(wB, n1, aB1);
-            aB2 = M::fma_(wB, n2, aB2); aB3 = M::fma_(wB, n3, aB3);
-            if (SCATTER) {
-                const Real wF = nw.b * s.F;
-                aS0 = M::fma_(wF, n0, aS0); aS1 = M::fma_(wF, n1, aS1);
-                aS2 = M::fma_(wF, n2, aS2); aS3 = M::fma_(wF, n3, aS3);
-            }
-        }
-        emit(0, h * M::fma_(K.aB[0], aB0, K.aS[0] * aS0));
-        emit(1, h * M::fma_(K.aB[1], aB1, K.aS[1] * aS1));
-        emit(2, h * M::fma_(K.aB[2], aB2, K.aS[2] * aS2));
-        emit(3, h * M::fma_(K.aB[3], aB3, K.aS[3] * aS3));
-    }
+    const LosGeometry<Real> G = los_geometry<Real>(dux, duy, duz, dox, doy, doz);
+    kelsall_group_a<Real, SCATTER, SHARE13>(K, tab, nodes, G, outside_mask, sub, L, emit);
     if (!HAS_RF) return;
-
-    // ---------------- ring (own grid) -----------------------------------------------------------
-    {
-        const double start = sphere_distance(bq, r_obs2, K.cutR_in, (outside_mask >> 8) & 1u);
-        const double stop = sphere_distance(bq, r_obs2, K.cutR_out, (outside_mask >> 9) & 1u);
-        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
-        Real aB = 0, aS = 0;
-        for (int k = sub; k < K.n_nodes; k += L) {
-            const Pair<Real> nw = nodes[k];
-            const NodeSource<Real> s =
-                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
-            const Real d = M::sqrt_(s.Rh2) - K.r_R;
-            const Real Zc = M::fma_(s.xh, K.rnx, M::fma_(s.yh, K.rny, s.zh * K.rnz));
-            const Real n = M::exp2_(M::fma_(d * d, K.r_c2, M::abs_(Zc) * K.r_c3));
-            aB = M::fma_(nw.b * s.B, n, aB);
-            if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
-        }
-        emit(4, h * M::fma_(K.aB[4], aB, K.aS[4] * aS));
-    }
-    // ---------------- feature (own grid) --------------------------------------------------------
-    {
-        const double start = sphere_distance(bq, r_obs2, K.cutF_in, (outside_mask >> 10) & 1u);
-        const double stop = sphere_distance(bq, r_obs2, K.cutF_out, (outside_mask >> 11) & 1u);
-        const Real h = Real(0.5 * (stop - start)), mid = Real(0.5 * (stop + start));
-        // rotate by -(theta_earth + theta_0): then atan2 gives the wrapped longitude offset directly
-        // (number_density.py:163-170; [-pi,pi) vs (-pi,pi] only differs at |delta| = pi where the
-        // squared offset is identical)
-        const double th = atan2(dey, dex) + (double)K.f_theta0;
-        const Real cr = Real(cos(th)), sr = Real(sin(th));
-        Real aB = 0, aS = 0;
-        for (int k = sub; k < K.n_nodes; k += L) {
-            const Pair<Real> nw = nodes[k];
-            const NodeSource<Real> s =
-                node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), ux, uy, uz, ox, oy, oz);
-            const Real d = M::sqrt_(s.Rh2) - K.f_R;
-            const Real Zc = M::fma_(s.xh, K.fnx, M::fma_(s.yh, K.fny, s.zh * K.fnz));
-            const Real xr = M::fma_(s.xh, cr, s.yh * sr), yr = M::fma_(s.yh, cr, -(s.xh * sr));
-            const Real dth = M::atan2_(yr, xr);
-            const Real e = M::fma_(d * d, K.f_c2, M::fma_(M::abs_(Zc), K.f_c3, dth * dth * K.f_c5));
-            const Real n = M::exp2_(e);
-            aB = M::fma_(nw.b * s.B, n, aB);
-            if (SCATTER) aS = M::fma_(nw.b * s.F, n, aS);
-        }
-        emit(5, h * M::fma_(K.aB[5], aB, K.aS[5] * aS));
-    }
+    emit(4, kelsall_ring<Real, SCATTER>(K, tab, nodes, G, outside_mask, sub, L));
+    emit(5, kelsall_feature<Real, SCATTER>(K, tab, nodes, G, dex, dey, outside_mask, sub, L));
 }
 
 }  // namespace zodi

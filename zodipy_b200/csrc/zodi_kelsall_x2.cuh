@@ -1,0 +1,135 @@
+// zodi_kelsall_x2.cuh - packed-fp32 variant of the fused Kelsall group (cloud + 3 bands).
+//
+// The scalar fused kernel is bound by the SM's issue slots (ncu: 88.7 % issue utilisation, XU pipe
+// 76.6 %, FMA pipe 65.6 %; profiles/r1_ncu_kelsall_fp32_nside1024.md): of ~117 warp-instructions
+// per quadrature node, 82 are plain fp32 multiply/add/fma.  Blackwell's packed FFMA2 / FMUL2 /
+// FADD2 (PTX `fma.rn.f32x2`; sm_100+) execute two fp32 operations per lane in ONE issue slot (at
+// half the instruction rate, so the FMA pipe load is unchanged).  Here every thread integrates
+// TWO lines of sight and keeps each per-node quantity as an (a, b) register pair, which halves
+// the issue slots of the arithmetic and leaves the XU (MUFU) pipe as the limiter.
+// Transcendentals stay scalar MUFU ops (there is no packed form); compares/selects stay scalar.
+//
+// Arithmetic is the same sequence of operations as kelsall_group_a<float> (zodi_kelsall.cuh), so
+// both kernels produce bit-identical results (tests/test_gpu_parity.py checks this).
+#pragma once
+
+#include "zodi_kelsall.cuh"
+
+namespace zodi {
+
+struct alignas(8) F2 { float x, y; };
+
+ZODI_HD F2 f2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+ZODI_HD F2 f2(float a) { return f2(a, a); }
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float2 as_f2(F2 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ F2 from_f2(float2 v) { return f2(v.x, v.y); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return from_f2(__ffma2_rn(as_f2(a), as_f2(b), as_f2(c))); }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { return from_f2(__fmul2_rn(as_f2(a), as_f2(b))); }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { return from_f2(__fadd2_rn(as_f2(a), as_f2(b))); }
+#else
+inline F2 fma2(F2 a, F2 b, F2 c) { return f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline F2 mul2(F2 a, F2 b) { return f2(a.x * b.x, a.y * b.y); }
+inline F2 add2(F2 a, F2 b) { return f2(a.x + b.x, a.y + b.y); }
+#endif
+ZODI_HD F2 fma2(F2 a, float b, F2 c) { return fma2(a, f2(b), c); }
+ZODI_HD F2 fma2(F2 a, float b, float c) { return fma2(a, f2(b), f2(c)); }
+ZODI_HD F2 fma2(F2 a, F2 b, float c) { return fma2(a, b, f2(c)); }
+ZODI_HD F2 mul2(F2 a, float b) { return mul2(a, f2(b)); }
+ZODI_HD F2 add2(F2 a, float b) { return add2(a, f2(b)); }
+
+// scalar (MUFU / select) helpers applied to both halves
+ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v.y)); }
+ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
+ZODI_HD F2 lg2_2(F2 v) { return f2(Math<float>::log2_(v.x), Math<float>::log2_(v.y)); }
+ZODI_HD F2 rsq_2(F2 v) { return f2(Math<float>::rsqrt_(v.x), Math<float>::rsqrt_(v.y)); }
+
+// Table lookup for two temperatures (same arithmetic as table_at<float>).
+ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
+    t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
+    const float magic = 12582912.0f;
+    const F2 s = add2(add2(t, -0.5f), magic);
+#if defined(__CUDA_ARCH__)
+    const int i0 = __float_as_int(s.x) - 0x4B400000, i1 = __float_as_int(s.y) - 0x4B400000;
+#else
+    int b0, b1;
+    memcpy(&b0, &s.x, 4);
+    memcpy(&b1, &s.y, 4);
+    const int i0 = b0 - 0x4B400000, i1 = b1 - 0x4B400000;
+#endif
+    const Pair<float> e0 = tab[i0], e1 = tab[i1];
+    const F2 frac = fma2(add2(s, -magic), -1.0f, t);  // t - (s - magic)
+    return fma2(f2(e0.b, e1.b), frac, f2(e0.a, e1.a));
+}
+
+// 1 - 2^-y for both halves (same switch and polynomial as Math<float>::one_minus_exp2_neg).
+ZODI_HD F2 one_minus_exp2_neg2(F2 y) {
+    const F2 small = mul2(y, fma2(y, fma2(y, 0.05550411f, -0.24022651f), 0.69314718f));
+    const F2 e = ex2_neg2(y);
+    const F2 direct = fma2(e, -1.0f, 1.0f);  // 1 - e
+    return f2(y.x < 0.04508422f ? small.x : direct.x, y.y < 0.04508422f ? small.y : direct.y);
+}
+
+ZODI_HD F2 band_radial2(F2 Rh2, float by) {
+    const F2 y = mul2(Rh2, by);
+    const F2 y2 = mul2(y, y), y4 = mul2(y2, y2), y5 = mul2(y4, y);
+    return one_minus_exp2_neg2(mul2(y5, y5));
+}
+
+ZODI_HD F2 band_vertical2(F2 xh, F2 yh, F2 zh, F2 rinv, float bx, float by, float bz, float c3) {
+    const F2 sz = mul2(fma2(xh, bx, fma2(yh, by, mul2(zh, bz))), rinv);
+    const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2);
+    return mul2(ex2_neg2(mul2(s4, s2)), fma2(s4, c3, 1.0f));
+}
+
+// Group A (cloud + band1..3, thermal only) for two lines of sight; emit(ci, value_a, value_b).
+template <bool SHARE13, typename Emit>
+ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>* tab,
+                                const Pair<float>* nodes, const LosGeometry<float>& Ga,
+                                const LosGeometry<float>& Gb, uint32_t outside_mask, Emit emit) {
+    float ha, mida, hb, midb;
+    los_interval<float>(Ga, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, ha, mida);
+    los_interval<float>(Gb, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, hb, midb);
+    const F2 h = f2(ha, hb), mid = f2(mida, midb);
+    const F2 ux = f2(Ga.ux, Gb.ux), uy = f2(Ga.uy, Gb.uy), uz = f2(Ga.uz, Gb.uz);
+    const F2 ox = f2(Ga.ox, Gb.ox), oy = f2(Ga.oy, Gb.oy), oz = f2(Ga.oz, Gb.oz);
+    F2 a0 = f2(0.f), a1 = f2(0.f), a2 = f2(0.f), a3 = f2(0.f);
+    for (int k = 0; k < K.n_nodes; ++k) {
+        const Pair<float> nw = nodes[k];
+        // shared source quantities (node_source<float, false>)
+        const F2 R_los = fma2(h, nw.a, mid);
+        const F2 xh = fma2(R_los, ux, ox), yh = fma2(R_los, uy, oy), zh = fma2(R_los, uz, oz);
+        const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
+        const F2 lgR = lg2_2(Rh2);
+        const F2 t = fma2(ex2_2(mul2(lgR, K.mhd)), K.t_scale, K.t_ofs);
+        const F2 B = table_at2(tab, t, K.t_top);
+        // bands
+        const F2 rinv = rsq_2(Rh2);
+        const F2 rad1 = band_radial2(Rh2, K.b_y[0]);
+        const F2 rad2 = band_radial2(Rh2, K.b_y[1]);
+        const F2 rad3 = SHARE13 ? rad1 : band_radial2(Rh2, K.b_y[2]);
+        const F2 n1 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]), mul2(rinv, rad1));
+        const F2 n2 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]), mul2(rinv, rad2));
+        const F2 n3 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]), mul2(rinv, rad3));
+        // cloud
+        const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
+        const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
+        const F2 Zc = fma2(xc, K.cnx, fma2(yc, K.cny, mul2(zc, K.cnz)));
+        const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
+        const F2 g_in = mul2(mul2(zeta, zeta), K.c_inv2mu), g_out = add2(zeta, -K.c_halfmu);
+        const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
+        const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
+        const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
+
+        const F2 wB = mul2(B, nw.b);
+        a0 = fma2(wB, n0, a0); a1 = fma2(wB, n1, a1);
+        a2 = fma2(wB, n2, a2); a3 = fma2(wB, n3, a3);
+    }
+    // scalar kernel: h * fma(aB, acc, aS * 0) == h * (aB * acc)
+    const F2 r0 = mul2(h, mul2(a0, K.aB[0])), r1 = mul2(h, mul2(a1, K.aB[1]));
+    const F2 r2 = mul2(h, mul2(a2, K.aB[2])), r3 = mul2(h, mul2(a3, K.aB[3]));
+    emit(0, r0.x, r0.y); emit(1, r1.x, r1.y); emit(2, r2.x, r2.y); emit(3, r3.x, r3.y);
+}
+
+}  // namespace zodi

@@ -12,6 +12,7 @@
 
 #include "zodi_device.cuh"
 #include "zodi_kelsall.cuh"
+#include "zodi_kelsall_x2.cuh"
 
 namespace zodi {
 
@@ -173,6 +174,64 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
                 store_out<Real>(args, ci, j, v);
         });
     if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
+}
+
+// Packed-fp32 fused kernel: every thread integrates TWO lines of sight (j and j + 256 of its CTA's
+// 512) with FFMA2/FMUL2/FADD2 for the cloud + bands group (zodi_kelsall_x2.cuh); ring and feature
+// reuse the scalar routines.  fp32, thermal-only, large-N (L = 1) case = the benchmarked path.
+template <bool HAS_RF, bool SHARE13>
+__global__ void __launch_bounds__(kThreads)
+zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
+                           const __grid_constant__ LaunchArgs args,
+                           const Pair<float>* __restrict__ g_table,
+                           const Pair<float>* __restrict__ g_nodes) {
+    __shared__ Pair<float> s_table[kFastMaxTemps];
+    __shared__ Pair<float> s_nodes[kFastMaxNodes];
+    for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
+    for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    const int64_t j0 = (int64_t)blockIdx.x * (2 * kThreads) + threadIdx.x, j1 = j0 + kThreads;
+    const bool act0 = j0 < args.n, act1 = j1 < args.n;
+    const int64_t jj0 = act0 ? j0 : args.n - 1, jj1 = act1 ? j1 : args.n - 1;
+
+    LosGeometry<float> G[2];
+    double ex[2] = {0.0, 0.0}, ey[2] = {0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int64_t jj = q ? jj1 : jj0;
+        double ux, uy, uz;
+        load_direction(args, jj, ux, uy, uz);
+        const int64_t jo = args.obs_per_sample ? jj : 0;
+        G[q] = los_geometry<float>(ux, uy, uz, args.obs[jo], args.obs[args.obs_stride + jo],
+                                   args.obs[2 * args.obs_stride + jo]);
+        if (HAS_RF) {
+            const int64_t je = args.earth_per_sample ? jj : 0;
+            ex[q] = args.earth[je];
+            ey[q] = args.earth[args.earth_stride + je];
+        }
+    }
+
+    float tot0 = 0.f, tot1 = 0.f;
+    auto emit2 = [&](int ci, float va, float vb) {
+        tot0 += va;
+        tot1 += vb;
+        if (args.return_comps) {
+            if (act0) store_out<float>(args, ci, j0, va);
+            if (act1) store_out<float>(args, ci, j1, vb);
+        }
+    };
+    kelsall_group_a_x2<SHARE13>(model, s_table, s_nodes, G[0], G[1], args.outside_mask, emit2);
+    if (HAS_RF) {
+        emit2(4, kelsall_ring<float, false>(model, s_table, s_nodes, G[0], args.outside_mask, 0, 1),
+              kelsall_ring<float, false>(model, s_table, s_nodes, G[1], args.outside_mask, 0, 1));
+        emit2(5, kelsall_feature<float, false>(model, s_table, s_nodes, G[0], ex[0], ey[0], args.outside_mask, 0, 1),
+              kelsall_feature<float, false>(model, s_table, s_nodes, G[1], ex[1], ey[1], args.outside_mask, 0, 1));
+    }
+    if (!args.return_comps) {
+        if (act0) store_out<float>(args, 0, j0, tot0);
+        if (act1) store_out<float>(args, 0, j1, tot1);
+    }
 }
 
 // Pixel-centre unit vectors only (same device routine the integrator uses in its prologue).
