@@ -39,6 +39,17 @@ ZODI_HD F2 fma2(F2 a, F2 b, float c) { return fma2(a, b, f2(c)); }
 ZODI_HD F2 mul2(F2 a, float b) { return mul2(a, f2(b)); }
 ZODI_HD F2 add2(F2 a, float b) { return add2(a, f2(b)); }
 
+// Warp-uniform "does any lane need this?" vote.  Band profiles are exactly zero over most of the
+// sky (exp of a large negative argument flushes to 0), and a branch that the WHOLE warp takes the
+// same way skips the MUFU instructions altogether - lane predication alone does not free the
+// XU pipe.  Exact: skipped values are the ones the MUFU would have flushed to zero.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }
+#else
+inline bool warp_any(bool p) { return p; }
+#endif
+constexpr float kEx2Underflow = 126.0f;  // ex2.approx.ftz(-y) == 0 for y > 126 (result < 2^-126)
+
 // scalar (MUFU / select) helpers applied to both halves
 ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v.y)); }
 ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
@@ -63,11 +74,14 @@ ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
     return fma2(f2(e0.b, e1.b), frac, f2(e0.a, e1.a));
 }
 
-// 1 - 2^-y for both halves (same switch and polynomial as Math<float>::one_minus_exp2_neg).
+// 1 - 2^-y for both halves (same switch and polynomial as Math<float>::one_minus_exp2_neg); the
+// MUFU pair is skipped when no lane of the warp is in the window where it matters.
 ZODI_HD F2 one_minus_exp2_neg2(F2 y) {
     const F2 small = mul2(y, fma2(y, fma2(y, 0.05550411f, -0.24022651f), 0.69314718f));
-    const F2 e = ex2_neg2(y);
-    const F2 direct = fma2(e, -1.0f, 1.0f);  // 1 - e
+    F2 direct = f2(1.0f);  // y > 126: 1 - 0
+    const bool need = (y.x >= 0.04508422f && y.x <= kEx2Underflow) ||
+                      (y.y >= 0.04508422f && y.y <= kEx2Underflow);
+    if (warp_any(need)) direct = fma2(ex2_neg2(y), -1.0f, 1.0f);  // 1 - e
     return f2(y.x < 0.04508422f ? small.x : direct.x, y.y < 0.04508422f ? small.y : direct.y);
 }
 
@@ -77,10 +91,16 @@ ZODI_HD F2 band_radial2(F2 Rh2, float by) {
     return one_minus_exp2_neg2(mul2(y5, y5));
 }
 
-ZODI_HD F2 band_vertical2(F2 xh, F2 yh, F2 zh, F2 rinv, float bx, float by, float bz, float c3) {
+// Adds w*B * n_band to acc, n_band = exp(-s^6) (1 + s^4/v) * (rinv * rad); skipped (n_band == 0)
+// when every lane of the warp is far enough from the band plane for exp(-s^6) to flush to zero.
+ZODI_HD void band_accumulate2(F2& acc, F2 wB, F2 xh, F2 yh, F2 zh, F2 rinv, F2 rinv_rad, float bx,
+                              float by, float bz, float c3) {
     const F2 sz = mul2(fma2(xh, bx, fma2(yh, by, mul2(zh, bz))), rinv);
-    const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2);
-    return mul2(ex2_neg2(mul2(s4, s2)), fma2(s4, c3, 1.0f));
+    const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2), s6 = mul2(s4, s2);
+    if (warp_any(s6.x <= kEx2Underflow || s6.y <= kEx2Underflow)) {
+        const F2 n = mul2(mul2(ex2_neg2(s6), fma2(s4, c3, 1.0f)), rinv_rad);
+        acc = fma2(wB, n, acc);
+    }
 }
 
 // Group A (cloud + band1..3, thermal only) for two lines of sight; emit(ci, value_a, value_b).
@@ -109,9 +129,10 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 rad1 = band_radial2(Rh2, K.b_y[0]);
         const F2 rad2 = band_radial2(Rh2, K.b_y[1]);
         const F2 rad3 = SHARE13 ? rad1 : band_radial2(Rh2, K.b_y[2]);
-        const F2 n1 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]), mul2(rinv, rad1));
-        const F2 n2 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]), mul2(rinv, rad2));
-        const F2 n3 = mul2(band_vertical2(xh, yh, zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]), mul2(rinv, rad3));
+        const F2 wB = mul2(B, nw.b);
+        band_accumulate2(a1, wB, xh, yh, zh, rinv, mul2(rinv, rad1), K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+        band_accumulate2(a2, wB, xh, yh, zh, rinv, mul2(rinv, rad2), K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+        band_accumulate2(a3, wB, xh, yh, zh, rinv, mul2(rinv, rad3), K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
         // cloud
         const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
         const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
@@ -121,10 +142,7 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
         const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
         const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
-
-        const F2 wB = mul2(B, nw.b);
-        a0 = fma2(wB, n0, a0); a1 = fma2(wB, n1, a1);
-        a2 = fma2(wB, n2, a2); a3 = fma2(wB, n3, a3);
+        a0 = fma2(wB, n0, a0);
     }
     // scalar kernel: h * fma(aB, acc, aS * 0) == h * (aB * acc)
     const F2 r0 = mul2(h, mul2(a0, K.aB[0])), r1 = mul2(h, mul2(a1, K.aB[1]));
