@@ -114,22 +114,36 @@ ZODI_HD NodeSource<Real> node_source(const KelsallModel<Real>& K, const Pair<Rea
     return s;
 }
 
-// exp(-s^6) * (1 + s^4 / v) for one band; (bx,by,bz) is the pre-scaled plane normal.
-template <typename Real>
-ZODI_HD Real band_vertical(Real xh, Real yh, Real zh, Real rinv, Real bx, Real by, Real bz, Real c3) {
+// Adds wB * n_band (and wF * n_band when scattering) to the accumulators, with
+// n_band = exp(-s^6) (1 + s^4/v) (rinv rad); (bx,by,bz) is the pre-scaled plane normal.  Skipped
+// (n_band == 0 exactly) when every lane of the warp is so far from the band plane that exp(-s^6)
+// underflows to zero.
+template <typename Real, bool SCATTER>
+ZODI_HD void band_accumulate(Real& accB, Real& accS, Real wB, Real wF, Real xh, Real yh, Real zh,
+                             Real rinv, Real rinv_rad, Real bx, Real by, Real bz, Real c3) {
     using M = Math<Real>;
     const Real sz = M::fma_(xh, bx, M::fma_(yh, by, zh * bz)) * rinv;  // sign irrelevant (even powers)
-    const Real s2 = sz * sz, s4 = s2 * s2;
-    return M::exp2_neg_(s4 * s2) * M::fma_(s4, c3, Real(1));
+    const Real s2 = sz * sz, s4 = s2 * s2, s6 = s4 * s2;
+    if (warp_any(s6 <= M::kEx2Underflow)) {
+        const Real n = (M::exp2_neg_(s6) * M::fma_(s4, c3, Real(1))) * rinv_rad;
+        accB = M::fma_(wB, n, accB);
+        if (SCATTER) accS = M::fma_(wF, n, accS);
+    }
 }
 
-// 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20)
+// 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20).
+// Beyond kRadialOne (R > ~1.25 delta_r: most of a line of sight that runs out to 5.2 AU) the term is
+// exactly 1; when the whole warp is there the power chain and the exponential are skipped.
 template <typename Real>
 ZODI_HD Real band_radial(Real Rh2, Real by) {
     using M = Math<Real>;
     const Real y = Rh2 * by;
-    const Real y2 = y * y, y4 = y2 * y2, y5 = y4 * y;
-    return M::one_minus_exp2_neg(y5 * y5);
+    Real rad = Real(1);
+    if (warp_any(y < M::kRadialOne)) {
+        const Real y2 = y * y, y4 = y2 * y2, y5 = y4 * y;
+        rad = M::one_minus_exp2_neg(y5 * y5);
+    }
+    return rad;
 }
 
 // Per-line-of-sight quantities shared by the component groups (prologue in double).
@@ -177,9 +191,10 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
         const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
         const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
         const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
-        const Real n1 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]) * (rinv * rad1);
-        const Real n2 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]) * (rinv * rad2);
-        const Real n3 = band_vertical<Real>(s.xh, s.yh, s.zh, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]) * (rinv * rad3);
+        const Real wB = nw.b * s.B, wF = SCATTER ? nw.b * s.F : Real(0);
+        band_accumulate<Real, SCATTER>(aB1, aS1, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad1, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+        band_accumulate<Real, SCATTER>(aB2, aS2, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad2, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+        band_accumulate<Real, SCATTER>(aB3, aS3, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad3, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
         // cloud
         const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
         const Real Rc2 = M::fma_(xc, xc, M::fma_(yc, yc, zc * zc));
@@ -188,14 +203,8 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
         const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
         const Real n0 = M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
 
-        const Real wB = nw.b * s.B;
-        aB0 = M::fma_(wB, n0, aB0); aB1 = M::fma_(wB, n1, aB1);
-        aB2 = M::fma_(wB, n2, aB2); aB3 = M::fma_(wB, n3, aB3);
-        if (SCATTER) {
-            const Real wF = nw.b * s.F;
-            aS0 = M::fma_(wF, n0, aS0); aS1 = M::fma_(wF, n1, aS1);
-            aS2 = M::fma_(wF, n2, aS2); aS3 = M::fma_(wF, n3, aS3);
-        }
+        aB0 = M::fma_(wB, n0, aB0);
+        if (SCATTER) aS0 = M::fma_(wF, n0, aS0);
     }
     emit(0, h * M::fma_(K.aB[0], aB0, K.aS[0] * aS0));
     emit(1, h * M::fma_(K.aB[1], aB1, K.aS[1] * aS1));

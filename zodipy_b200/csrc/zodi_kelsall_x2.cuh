@@ -39,17 +39,6 @@ ZODI_HD F2 fma2(F2 a, F2 b, float c) { return fma2(a, b, f2(c)); }
 ZODI_HD F2 mul2(F2 a, float b) { return mul2(a, f2(b)); }
 ZODI_HD F2 add2(F2 a, float b) { return add2(a, f2(b)); }
 
-// Warp-uniform "does any lane need this?" vote.  Band profiles are exactly zero over most of the
-// sky (exp of a large negative argument flushes to 0), and a branch that the WHOLE warp takes the
-// same way skips the MUFU instructions altogether - lane predication alone does not free the
-// XU pipe.  Exact: skipped values are the ones the MUFU would have flushed to zero.
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p); }
-#else
-inline bool warp_any(bool p) { return p; }
-#endif
-constexpr float kEx2Underflow = 126.0f;  // ex2.approx.ftz(-y) == 0 for y > 126 (result < 2^-126)
-
 // scalar (MUFU / select) helpers applied to both halves
 ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v.y)); }
 ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
@@ -79,16 +68,23 @@ ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
 ZODI_HD F2 one_minus_exp2_neg2(F2 y) {
     const F2 small = mul2(y, fma2(y, fma2(y, 0.05550411f, -0.24022651f), 0.69314718f));
     F2 direct = f2(1.0f);  // y > 126: 1 - 0
-    const bool need = (y.x >= 0.04508422f && y.x <= kEx2Underflow) ||
-                      (y.y >= 0.04508422f && y.y <= kEx2Underflow);
+    const bool need = (y.x >= 0.04508422f && y.x <= Math<float>::kEx2Underflow) ||
+                      (y.y >= 0.04508422f && y.y <= Math<float>::kEx2Underflow);
     if (warp_any(need)) direct = fma2(ex2_neg2(y), -1.0f, 1.0f);  // 1 - e
     return f2(y.x < 0.04508422f ? small.x : direct.x, y.y < 0.04508422f ? small.y : direct.y);
 }
 
+// y = R^2 log2e^(1/10) / delta_r^2, so y^10 = log2e (R/delta_r)^20.  Beyond y = 1.6225 (R > 1.25 delta_r,
+// most of a line of sight that runs out to 5.2 AU) y^10 > 126 and the term is exactly 1: when the whole
+// warp is there the power chain, the polynomial and the MUFU pair are skipped.
 ZODI_HD F2 band_radial2(F2 Rh2, float by) {
     const F2 y = mul2(Rh2, by);
-    const F2 y2 = mul2(y, y), y4 = mul2(y2, y2), y5 = mul2(y4, y);
-    return one_minus_exp2_neg2(mul2(y5, y5));
+    F2 rad = f2(1.0f);
+    if (warp_any(y.x < Math<float>::kRadialOne || y.y < Math<float>::kRadialOne)) {
+        const F2 y2 = mul2(y, y), y4 = mul2(y2, y2), y5 = mul2(y4, y);
+        rad = one_minus_exp2_neg2(mul2(y5, y5));
+    }
+    return rad;
 }
 
 // Adds w*B * n_band to acc, n_band = exp(-s^6) (1 + s^4/v) * (rinv * rad); skipped (n_band == 0)
@@ -97,7 +93,7 @@ ZODI_HD void band_accumulate2(F2& acc, F2 wB, F2 xh, F2 yh, F2 zh, F2 rinv, F2 r
                               float by, float bz, float c3) {
     const F2 sz = mul2(fma2(xh, bx, fma2(yh, by, mul2(zh, bz))), rinv);
     const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2), s6 = mul2(s4, s2);
-    if (warp_any(s6.x <= kEx2Underflow || s6.y <= kEx2Underflow)) {
+    if (warp_any(s6.x <= Math<float>::kEx2Underflow || s6.y <= Math<float>::kEx2Underflow)) {
         const F2 n = mul2(mul2(ex2_neg2(s6), fma2(s4, c3, 1.0f)), rinv_rad);
         acc = fma2(wB, n, acc);
     }

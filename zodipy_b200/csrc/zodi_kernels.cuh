@@ -179,8 +179,8 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
 // Packed-fp32 fused kernel: every thread integrates TWO lines of sight (j and j + 256 of its CTA's
 // 512) with FFMA2/FMUL2/FADD2 for the cloud + bands group (zodi_kelsall_x2.cuh); ring and feature
 // reuse the scalar routines.  fp32, thermal-only, large-N (L = 1) case = the benchmarked path.
-template <bool HAS_RF, bool SHARE13>
-__global__ void __launch_bounds__(kThreads)
+template <bool HAS_RF, bool SHARE13, int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS)
 zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
                            const __grid_constant__ LaunchArgs args,
                            const Pair<float>* __restrict__ g_table,
