@@ -182,8 +182,13 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
     Real h, mid;
     los_interval<Real>(G, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, h, mid);
     Real aB0 = 0, aB1 = 0, aB2 = 0, aB3 = 0, aS0 = 0, aS1 = 0, aS2 = 0, aS3 = 0;
-    for (int k = sub; k < K.n_nodes; k += L) {
-        const Pair<Real> nw = nodes[k];
+    // Warp-uniform trip count: the body contains warp votes (warp_any), so every lane must run the
+    // same number of iterations even when n_nodes is not a multiple of L; surplus iterations
+    // re-evaluate the last node with weight 0.
+    for (int k0 = 0; k0 < K.n_nodes; k0 += L) {
+        const int k = k0 + sub;
+        Pair<Real> nw = nodes[k < K.n_nodes ? k : K.n_nodes - 1];
+        if (k >= K.n_nodes) nw.b = Real(0);
         const NodeSource<Real> s = node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), G.ux, G.uy,
                                                               G.uz, G.ox, G.oy, G.oz);
         // bands: centred on the Sun -> share R
