@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Kernel-resident throughput + oracle parity for the five BASELINE.json configurations.
+
+Informational companion of bench.py (which times only the headline configuration): for each
+config, inputs are generated on the device, the fp32 and fp64 modes are timed with CUDA events and a
+random subset is checked against the CPU oracle.  Prints one JSON object per config.
+
+    python benchmarks/baseline_configs.py [--max-n 2e8] [--skip-fp64-above 6e7]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import zodi_oracle as oracle  # noqa: E402
+import zodipy_b200 as zp  # noqa: E402
+from zodipy_b200 import engine, healpix  # noqa: E402
+
+EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])
+
+
+def healpix_dirs(nside, dev):
+    u = torch.empty((3, 12 * nside * nside), dtype=torch.float64, device=dev)
+    _cabi = engine._cabi
+    _cabi.check(_cabi.load().zodi_healpix_vectors(dev.index, nside, 0, u.shape[1], None, u.data_ptr(),
+                                                  u.shape[1], _cabi.MEM_DEVICE, None))
+    torch.cuda.synchronize()
+    return u
+
+
+def tod_inputs(n, dev):
+    """Synthetic year of time-ordered data: spin-scan-like pointing, Earth on a slightly eccentric
+    orbit, observer = SEMB-L2-like scaling of Earth plus a small halo orbit (per-sample arrays)."""
+    i = torch.arange(n, dtype=torch.float64, device=dev)
+    t = i / n  # years
+    lon_e = 2 * np.pi * t + 1.7
+    r_e = 1.0 - 0.0167 * torch.cos(lon_e - 1.8)
+    earth = torch.stack([r_e * torch.cos(lon_e), r_e * torch.sin(lon_e), 1e-5 * torch.sin(3 * lon_e)])
+    obs = earth * 1.01 + torch.stack([torch.zeros_like(t), torch.zeros_like(t), 0.002 * torch.cos(40 * lon_e)])
+    spin = 2 * np.pi * 525600.0 * t  # one rotation per minute
+    colat = np.radians(85.0) + np.radians(7.5) * torch.sin(2 * np.pi * 8760.0 * t)
+    # pointing = rotate (colat, spin) about the anti-sun axis
+    ax = -earth / torch.linalg.vector_norm(earth, dim=0, keepdim=True)
+    z = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64, device=dev).reshape(3, 1).expand(3, n)
+    e1 = torch.linalg.cross(ax, z, dim=0)
+    e1 = e1 / torch.linalg.vector_norm(e1, dim=0, keepdim=True)
+    e2 = torch.linalg.cross(ax, e1, dim=0)
+    u = torch.cos(colat) * ax + torch.sin(colat) * (torch.cos(spin) * e1 + torch.sin(spin) * e2)
+    u = u / torch.linalg.vector_norm(u, dim=0, keepdim=True)
+    return u.contiguous(), obs.contiguous(), earth.contiguous()
+
+
+def time_mode(dm, u, obs, earth, precision, out_dtype, reps):
+    out = dm.evaluate(u, obs, earth, precision=precision, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        dm.evaluate(u, obs, earth, precision=precision, out=out, out_dtype=out_dtype)
+    b.record()
+    torch.cuda.synchronize()
+    return out, a.elapsed_time(b) / reps
+
+
+def run(label, model, u, obs, earth, skip_fp64_above):
+    dm = model.device_model
+    n = u.shape[1]
+    units = n * model.ncomps * len(model.spec["points"])
+    sel = np.sort(np.random.default_rng(2).choice(n, 1500, replace=False))
+    sel_t = torch.as_tensor(sel, device=u.device)
+    per_sample = obs.shape[1] == n
+    u_s = u[:, sel_t].cpu().numpy()
+    obs_s = obs[:, sel_t].cpu().numpy() if per_sample else obs.cpu().numpy()
+    earth_s = earth[:, sel_t].cpu().numpy() if per_sample else earth.cpu().numpy()
+    # the oracle derives its early-out flags from the subset's observers; they equal the global
+    # ones here because every synthetic observer stays inside all outer cutoffs
+    ref = oracle.evaluate(model.spec, u_s, obs_s, earth_s).sum(axis=0)
+    res = {"config": label, "n_los": n, "ncomps": model.ncomps, "evaluations": units, "kernel": dm.kernel_name}
+    for precision, out_dtype, tol in (("fp32", np.float32, 1e-5), ("fp64", np.float64, 1e-10)):
+        if precision == "fp64" and n > skip_fp64_above:
+            continue
+        reps = 5 if precision == "fp32" else 2
+        out, ms = time_mode(dm, u, obs, earth, precision, out_dtype, reps)
+        got = out[sel_t].double().cpu().numpy()
+        err = float(np.max(np.abs(got - ref) / np.abs(ref)))
+        res[precision] = {"ms": ms, "evals_per_s": units / (ms * 1e-3), "los_per_s": n / (ms * 1e-3),
+                          "max_rel_err_vs_oracle": err, "tolerance": tol, "ok": bool(err <= tol)}
+    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--max-n", type=float, default=2.1e8)
+    ap.add_argument("--skip-fp64-above", type=float, default=6e7)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    earth = torch.as_tensor(EARTH, device=dev)
+    Q = zp.Quantity
+
+    run("1: dirbe 25um nside=64", zp.Model(Q(25.0, "um")), healpix_dirs(64, dev), earth, earth, args.skip_fp64_above)
+    x = np.linspace(9.0, 15.0, 10)
+    w = np.exp(-0.5 * ((x - 12.0) / 1.5) ** 2)
+    run("2: dirbe 12um 10-sample bandpass nside=512", zp.Model(Q(x, "um"), weights=w), healpix_dirs(512, dev),
+        earth, earth, args.skip_fp64_above)
+    run("3: planck18 857GHz nside=2048", zp.Model(Q(857.0, "GHz"), name="planck18"), healpix_dirs(2048, dev),
+        earth, earth, args.skip_fp64_above)
+    n_tod = int(min(1e8, args.max_n))
+    u, obs, ear = tod_inputs(n_tod, dev)
+    run(f"4: TOD {n_tod:.0e} samples dirbe 25um per-sample obs/earth", zp.Model(Q(25.0, "um")), u, obs, ear,
+        args.skip_fp64_above)
+    del u, obs, ear
+    torch.cuda.empty_cache()
+    if args.max_n >= 12 * 4096 * 4096:
+        run("5: planck13 545GHz nside=4096", zp.Model(Q(545.0, "GHz"), name="planck13"), healpix_dirs(4096, dev),
+            earth, earth, 3e8)
+    # extra: scattering branch and the generic kernel (RRM)
+    run("extra: dirbe 1.25um (scattering) nside=512", zp.Model(Q(1.25, "um")), healpix_dirs(512, dev), earth, earth,
+        args.skip_fp64_above)
+    run("extra: rrm-experimental 25um nside=256 (generic kernel)", zp.Model(Q(25.0, "um"), name="rrm-experimental"),
+        healpix_dirs(256, dev), earth, earth, args.skip_fp64_above)
+
+
+if __name__ == "__main__":
+    main()
