@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-store epilogue (default) or separate NCCL all-gather")
+    ap.add_argument("--shard", default="auto", choices=["auto", "contiguous", "cyclic"],
+                    help="N>1 shard layout: contiguous (np.array_split rule) or block-cyclic "
+                         "(load-balanced; default with the fused gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -217,12 +220,23 @@ def run_b200(args):
     npix = healpix.nside2npix(args.nside)
     ncomps = model.ncomps
     lo, hi = sharding.split_bounds(npix, world)[rank]
-    n_local = hi - lo
+    fused = world > 1 and args.gather == "fused"
+    cyclic = fused and args.shard in ("auto", "cyclic")
     units_total = npix * ncomps * DEG
 
     # ---- inputs: pinned host copy (for e2e) and HBM-resident copy (for value) ----
-    u_host = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
-    healpix.full_sky_vectors(args.nside, lo, hi, out=u_host.numpy())
+    if cyclic:
+        # block-cyclic shard: contiguous RING shards are latitude bands of unequal cost
+        shard_idx = sharding.cyclic_indices(npix, world, rank)
+        n_local = shard_idx.size
+        u_host = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
+        for c0 in range(0, n_local, 1 << 22):
+            u_host.numpy()[:, c0:c0 + (1 << 22)] = healpix.pix2vec_ring(args.nside, shard_idx[c0:c0 + (1 << 22)])
+    else:
+        shard_idx = None
+        n_local = hi - lo
+        u_host = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
+        healpix.full_sky_vectors(args.nside, lo, hi, out=u_host.numpy())
     u_dev = u_host.to(dev, non_blocking=True)
     obs_dev = torch.as_tensor(EARTH, device=dev)
     flags = dm.outside_flags(EARTH)
@@ -232,8 +246,8 @@ def run_b200(args):
 
     # N > 1: the kernel stores its slice into every rank's full map (fused all-gather over NVLink
     # peer memory); --gather nccl uses a separate NCCL all-gather instead.
-    fused = world > 1 and args.gather == "fused"
-    peer_map = sharding.PeerMap(npix, 1, out_dtype, local_rank) if fused else None
+    peer_map = sharding.PeerMap(npix, 1, out_dtype, local_rank,
+                                cyclic_block=sharding.CYCLIC_BLOCK if cyclic else 0) if fused else None
 
     def step():
         if fused:
@@ -285,11 +299,20 @@ def run_b200(args):
     launches = engine.kernel_launch_count() - launches0
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
-        # every rank must hold the complete map: compare with an independent NCCL all-gather
+        # every rank must hold the complete map: compare with an independent evaluation
         dm.evaluate(u_dev, obs_dev, obs_dev, precision=precision, out=out_local, out_dtype=out_dtype,
                     outside_flags=flags)
-        check = sharding.allgather_map(out_local, npix)
-        assert torch.equal(full, check), "assembled map differs from the all-gathered reference"
+        if cyclic:
+            mine = torch.as_tensor(shard_idx, device=dev)
+            assert torch.equal(full[mine], out_local), "own shard of the assembled map is wrong"
+            probe = torch.as_tensor(np.sort(np.random.default_rng(7).choice(npix, 1 << 16, replace=False)), device=dev)
+            u_probe = torch.as_tensor(healpix.pix2vec_ring(args.nside, probe.cpu().numpy()), device=dev)
+            ref_probe = dm.evaluate(u_probe, obs_dev, obs_dev, precision=precision, out_dtype=out_dtype,
+                                    outside_flags=flags)
+            assert torch.allclose(full[probe], ref_probe, rtol=2e-6, atol=0), "assembled map is wrong"
+        else:
+            check = sharding.allgather_map(out_local, npix)
+            assert torch.equal(full, check), "assembled map differs from the all-gathered reference"
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
     if world > 1:
         t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -336,7 +359,8 @@ def run_b200(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        hp_err = float(np.max(np.abs(out_np - out_local.cpu().numpy()) / np.abs(out_np)))
+        same = (full[lo:hi] if world > 1 else out_local).cpu().numpy()  # contiguous pixels lo..hi
+        hp_err = float(np.max(np.abs(out_np - same) / np.abs(out_np)))
         e2e["healpix_entry"] = {
             "value": units_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_e2e,
             "h2d_bytes_per_step": 48 * world, "d2h_bytes_per_step": int(npix * out_host.element_size()),
@@ -411,7 +435,9 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f64",
-        "data": "synthetic", "config": workload_config(args.nside, world, precision, args.gather),
+        "data": "synthetic",
+        "config": dict(workload_config(args.nside, world, precision, args.gather),
+                       shard_layout=("block-cyclic, 65536-line blocks" if cyclic else "contiguous (np.array_split)")),
         "pixels_per_s": npix / (ms_per_step * 1e-3),
         "max_rel_err_vs_oracle": max_rel, "tolerance": 1e-5 if precision == "fp32" else 1e-10,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
@@ -427,10 +453,35 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torchrun notices)
+    # write to fd 1 directly, so park fd 1 on stderr while running and emit the line at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+
+    def capture_print(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            builtins_print(*a, **k)
+
+    builtins_print = builtins.print
+    builtins.print = capture_print
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        builtins.print = builtins_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in lines:
+        if line.startswith("{"):
+            print(line, flush=True)
 
 
 if __name__ == "__main__":

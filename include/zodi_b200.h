@@ -147,6 +147,14 @@ typedef struct {
     void* peer_out[ZODI_MAX_PEERS];
     int64_t peer_offset;
     int64_t peer_stride;
+    /* Block-cyclic shard layout (load balance: contiguous shards of a RING map are latitude bands
+     * of unequal cost).  When cyclic_block > 0, line of sight j of this call is element
+     *     g(j) = ((j / cyclic_block) * cyclic_parts + cyclic_rank) * cyclic_block + j % cyclic_block
+     * of the global job: peer stores go to peer_offset + g(j) and zodi_evaluate_healpix integrates
+     * pixel ipix_start + g(j).  Input arrays and `out` stay indexed by the local j. */
+    int64_t cyclic_block;
+    int32_t cyclic_parts;
+    int32_t cyclic_rank;
 } zodi_eval_args;
 
 /* HEALPix map evaluation with directions generated on the device (no (3, N) upload):

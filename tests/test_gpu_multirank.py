@@ -59,6 +59,25 @@ def _worker(rank, world, port, backend, case_id, per_sample, precision, use_peer
             result["fused"] = pm.finish().cpu().numpy()
             dist.barrier()
             pm.close()
+        if use_peer_map:
+            # block-cyclic shards + on-device HEALPix directions + fused peer stores
+            nside, block = 16, 64
+            npix = 12 * nside * nside
+            pmc = sharding.PeerMap(npix, dm.ncomps, np.float64, dev_index, cyclic_block=block)
+            dm.evaluate_healpix(nside, a["obs"][:, :1], a["earth"][:, :1], return_comps=True,
+                                precision=precision, peer_map=pmc)
+            result["cyclic_healpix"] = pmc.finish().cpu().numpy()
+            # array-seam inputs in block-cyclic order
+            from zodipy_b200 import healpix
+
+            idx = sharding.cyclic_indices(npix, world, rank, block)
+            u_c = torch.as_tensor(healpix.pix2vec_ring(nside, idx), device=dev)
+            dm.evaluate(u_c, torch.as_tensor(a["obs"][:, :1].copy(), device=dev),
+                        torch.as_tensor(a["earth"][:, :1].copy(), device=dev), return_comps=True,
+                        precision=precision, peer_map=pmc)
+            result["cyclic_array"] = pmc.finish().cpu().numpy()
+            dist.barrier()
+            pmc.close()
         queue.put((rank, result))
     except Exception as err:
         queue.put((rank, err))
@@ -117,6 +136,10 @@ def test_fused_peer_store_equals_allgather(case_id, per_sample):
     case, a = golden_case(case_id)
     single = engine.DeviceModel(case["spec"], 0).evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
     results = _run(world, "nccl", case_id, per_sample, "fp64", True)
+    hp_single = engine.DeviceModel(case["spec"], 0).evaluate_healpix(
+        16, a["obs"][:, :1], a["earth"][:, :1], return_comps=True)
     for r in range(world):
         np.testing.assert_array_equal(results[r]["gathered"], single)
         np.testing.assert_array_equal(results[r]["fused"], single)
+        np.testing.assert_array_equal(results[r]["cyclic_healpix"], hp_single)
+        np.testing.assert_array_equal(results[r]["cyclic_array"], hp_single)

@@ -69,6 +69,7 @@ class EvalArgs(C.Structure):
         ("n_peers", C.c_int32), ("reserved", C.c_int32),
         ("peer_out", C.c_void_p * MAX_PEERS),
         ("peer_offset", C.c_int64), ("peer_stride", C.c_int64),
+        ("cyclic_block", C.c_int64), ("cyclic_parts", C.c_int32), ("cyclic_rank", C.c_int32),
     ]
 
 

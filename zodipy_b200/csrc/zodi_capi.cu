@@ -307,6 +307,11 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
     if (!a) return fail(ZODI_ERR_INVALID, "eval args are NULL");
     if (a->n < 0) return fail(ZODI_ERR_INVALID, "n=%lld is negative", (long long)a->n);
     if (a->n == 0) return ZODI_OK;
+    if (a->cyclic_block < 0 || (a->cyclic_block > 0 && (a->cyclic_parts < 1 || a->cyclic_rank < 0 ||
+                                                        a->cyclic_rank >= a->cyclic_parts)))
+        return fail(ZODI_ERR_INVALID, "bad block-cyclic layout");
+    if (a->cyclic_block > 0 && a->memory != ZODI_MEM_DEVICE)
+        return fail(ZODI_ERR_INVALID, "block-cyclic layout needs ZODI_MEM_DEVICE");
     if (a->n_peers < 0 || a->n_peers > ZODI_MAX_PEERS)
         return fail(ZODI_ERR_INVALID, "n_peers=%d outside [0, %d]", a->n_peers, ZODI_MAX_PEERS);
     if (a->n_peers > 0) {
@@ -314,7 +319,8 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
             return fail(ZODI_ERR_INVALID, "peer output needs ZODI_MEM_DEVICE inputs");
         for (int p = 0; p < a->n_peers; ++p)
             if (!a->peer_out[p]) return fail(ZODI_ERR_INVALID, "peer_out[%d] is NULL", p);
-        if (a->peer_offset < 0 || (a->return_comps && a->peer_stride < a->peer_offset + a->n))
+        if (a->peer_offset < 0 || (a->return_comps && a->cyclic_block == 0 &&
+                                   a->peer_stride < a->peer_offset + a->n))
             return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
     }
     if ((need_u && !a->u) || !a->obs || !a->earth || (!a->out && a->n_peers == 0))
@@ -339,6 +345,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
 }
 
 void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
+    la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0;
     la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = 0.0;
     if (!hp) return;
@@ -555,6 +562,7 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
     la.n_peers = a->n_peers; la.peer_offset = a->peer_offset; la.peer_stride = a->peer_stride;
     for (int p = 0; p < ZODI_MAX_PEERS; ++p) la.peer_out[p] = p < a->n_peers ? a->peer_out[p] : nullptr;
     set_healpix(la, hp, 0);
+    la.cyc_block = a->cyclic_block; la.cyc_parts = a->cyclic_parts; la.cyc_rank = a->cyclic_rank;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
     return ZODI_OK;
 }
@@ -573,7 +581,13 @@ static int check_healpix(int64_t nside, int64_t ipix_start, int64_t n, int nest)
 
 int zodi_evaluate_healpix(zodi_model_t m, const zodi_healpix_args* hp) {
     if (!hp) return fail(ZODI_ERR_INVALID, "healpix args are NULL");
-    int rc = check_healpix(hp->nside, hp->ipix_start, hp->base.n, hp->nest);
+    int64_t span = hp->base.n;  // pixels [ipix_start, ipix_start + span) must exist
+    if (hp->base.cyclic_block > 0 && hp->base.n > 0 && hp->base.cyclic_parts >= 1) {
+        const int64_t j = hp->base.n - 1, lb = j / hp->base.cyclic_block;
+        span = (lb * hp->base.cyclic_parts + hp->base.cyclic_rank) * hp->base.cyclic_block +
+               (j - lb * hp->base.cyclic_block) + 1;
+    }
+    int rc = check_healpix(hp->nside, hp->ipix_start, span, hp->nest);
     if (rc) return rc;
     if (hp->base.n_obs != 1 && hp->base.n_obs != hp->base.n)
         return fail(ZODI_ERR_INVALID, "n_obs must be 1 or n");

@@ -35,14 +35,23 @@ struct LaunchArgs {
     // on-device directions: HEALPix RING pixel hp_start + j (u is ignored when hp_nside > 0)
     int64_t hp_nside;     int64_t hp_start;
     int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel vector
+    // block-cyclic shard layout (see zodi_eval_args.cyclic_block); 0 = identity
+    int64_t cyc_block;    int cyc_parts;      int cyc_rank;
 };
+
+// Global index of local line of sight j under the (optional) block-cyclic layout.
+__device__ __forceinline__ int64_t global_index(const LaunchArgs& a, int64_t j) {
+    if (a.cyc_block <= 0) return j;
+    const int64_t lb = j / a.cyc_block;
+    return (lb * a.cyc_parts + a.cyc_rank) * a.cyc_block + (j - lb * a.cyc_block);
+}
 
 // Direction of line of sight j: loaded (reference array seam) or generated from the pixel index.
 __device__ __forceinline__ void load_direction(const LaunchArgs& a, int64_t jj, double& ux, double& uy,
                                                double& uz) {
     if (a.hp_nside > 0) {
         double x, y, z;
-        healpix_ring_pix2vec(a.hp_nside, a.hp_start + jj, x, y, z);
+        healpix_ring_pix2vec(a.hp_nside, a.hp_start + global_index(a, jj), x, y, z);
         if (a.hp_rotate) {
             ux = a.hp_rot[0] * x + a.hp_rot[1] * y + a.hp_rot[2] * z;
             uy = a.hp_rot[3] * x + a.hp_rot[4] * y + a.hp_rot[5] * z;
@@ -62,7 +71,7 @@ __device__ __forceinline__ void load_direction(const LaunchArgs& a, int64_t jj, 
 template <typename Real>
 __device__ __forceinline__ void store_out(const LaunchArgs& a, int ci, int64_t j, Real v) {
     if (a.n_peers > 0) {
-        const int64_t idx = (int64_t)ci * a.peer_stride + a.peer_offset + j;
+        const int64_t idx = (int64_t)ci * a.peer_stride + a.peer_offset + global_index(a, j);
         for (int p = 0; p < a.n_peers; ++p) {
             if (a.out_f32) reinterpret_cast<float*>(a.peer_out[p])[idx] = (float)v;
             else reinterpret_cast<double*>(a.peer_out[p])[idx] = (double)v;

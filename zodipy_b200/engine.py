@@ -157,7 +157,7 @@ class DeviceModel:
             stream = None
         if n == 0:
             return out
-        if peer_map is not None and peer_map.offset + n > peer_map.n_total:
+        if peer_map is not None and peer_map.cyclic is None and peer_map.offset + n > peer_map.n_total:
             raise ValueError("slice does not fit the peer map")
 
         if outside_flags is None:
@@ -189,6 +189,8 @@ class DeviceModel:
             for i, ptr in enumerate(peer_map.pointers):
                 args.peer_out[i] = ptr
             args.peer_offset, args.peer_stride = peer_map.offset, peer_map.n_total
+            if peer_map.cyclic is not None:
+                args.cyclic_block, args.cyclic_parts, args.cyclic_rank = peer_map.cyclic
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 
@@ -211,6 +213,11 @@ class DeviceModel:
         if not 0 <= lo <= hi <= npix:
             raise ValueError("pix_range outside the map")
         n = hi - lo
+        if peer_map is not None and peer_map.cyclic is not None:
+            # block-cyclic shard of [lo, hi): this rank integrates its share; the kernel maps j -> pixel
+            from .sharding import cyclic_count
+
+            n = cyclic_count(hi - lo, peer_map.cyclic[1], peer_map.cyclic[2], peer_map.cyclic[0])
         obs_h = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(3, 1))
         earth_h = obs_h if earth is None else np.ascontiguousarray(
             np.asarray(earth, dtype=np.float64).reshape(3, 1))
@@ -265,6 +272,8 @@ class DeviceModel:
             for i, ptr in enumerate(peer_map.pointers):
                 a.peer_out[i] = ptr
             a.peer_offset, a.peer_stride = peer_map.offset, peer_map.n_total
+            if peer_map.cyclic is not None:
+                a.cyclic_block, a.cyclic_parts, a.cyclic_rank = peer_map.cyclic
         h.nside, h.ipix_start, h.nest = nside, lo, 0
         if rot is not None:
             r = np.asarray(rot, dtype=np.float64).reshape(9)

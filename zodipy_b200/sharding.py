@@ -27,6 +27,28 @@ def split_bounds(n: int, parts: int) -> list[tuple[int, int]]:
     return bounds
 
 
+CYCLIC_BLOCK = 1 << 16
+
+
+def cyclic_count(n: int, parts: int, rank: int, block: int = CYCLIC_BLOCK) -> int:
+    """Number of elements rank ``rank`` owns under the block-cyclic layout (blocks rank,
+    rank + parts, ... of ``block`` elements; only the globally last block may be short)."""
+    nblocks = -(-n // block)
+    mine = len(range(rank, nblocks, parts))
+    if mine == 0:
+        return 0
+    last_global = rank + (mine - 1) * parts
+    short = block - (n - last_global * block) if last_global == nblocks - 1 else 0
+    return mine * block - max(short, 0)
+
+
+def cyclic_indices(n: int, parts: int, rank: int, block: int = CYCLIC_BLOCK) -> np.ndarray:
+    """Global indices g(j), j = 0..count-1, of rank ``rank``'s block-cyclic shard (the same map the
+    kernels apply: ``((j // block) * parts + rank) * block + j % block``)."""
+    j = np.arange(cyclic_count(n, parts, rank, block), dtype=np.int64)
+    return ((j // block) * parts + rank) * block + j % block
+
+
 def padded_count(n: int, parts: int) -> int:
     """Equal per-rank slot length used by the all-gather (ceil(n / parts))."""
     return -(-n // parts)
@@ -117,7 +139,8 @@ class PeerMap:
     rank.  One process per GPU, ranks of one NVSwitch box.
     """
 
-    def __init__(self, n_total: int, rows: int, dtype, device_index: int, group=None):
+    def __init__(self, n_total: int, rows: int, dtype, device_index: int, group=None,
+                 cyclic_block: int = 0):
         import ctypes as C
 
         import torch
@@ -133,8 +156,9 @@ class PeerMap:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > _cabi.MAX_PEERS:
             raise ValueError(f"at most {_cabi.MAX_PEERS} peers")
-        lo, _ = split_bounds(self.n_total, world)[rank]
-        self.offset = lo
+        # contiguous np.array_split shards by default; block-cyclic (load-balanced) on request
+        self.cyclic = (int(cyclic_block), world, rank) if cyclic_block else None
+        self.offset = 0 if self.cyclic else split_bounds(self.n_total, world)[rank][0]
         nbytes = self.rows * self.n_total * self.dtype.itemsize
         own = C.c_void_p()
         handle = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES)()
