@@ -142,4 +142,5 @@ def test_fused_peer_store_equals_allgather(case_id, per_sample):
         np.testing.assert_array_equal(results[r]["gathered"], single)
         np.testing.assert_array_equal(results[r]["fused"], single)
         np.testing.assert_array_equal(results[r]["cyclic_healpix"], hp_single)
-        np.testing.assert_array_equal(results[r]["cyclic_array"], hp_single)
+        # directions from the host pix2vec differ from the device routine in the last ulp
+        np.testing.assert_allclose(results[r]["cyclic_array"], hp_single, rtol=1e-12)
