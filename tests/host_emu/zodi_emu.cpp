@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../zodipy_b200/csrc/zodi_model_build.hpp"
+#include "../../zodipy_b200/csrc/zodi_kelsall_x2.cuh"
 
 using namespace zodi;
 
@@ -65,6 +66,37 @@ static void run_kelsall(const KelsallModel<Real>& K, const std::vector<Pair<Real
     }
 }
 
+// Packed (two lines of sight per "thread") routines of zodi_kelsall_x2.cuh, fp32 thermal-only.
+static void run_kelsall_x2(const KelsallModel<float>& K, const std::vector<Pair<float>>& tab,
+                           const std::vector<Pair<float>>& nodes, int64_t n, const double* u,
+                           const double* obs, int64_t n_obs, const double* earth, int64_t n_earth,
+                           const uint8_t* flags, double* out) {
+    uint32_t mask = 0;
+    for (int c = 0; c < K.n_comps; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    for (int64_t j0 = 0; j0 < n; j0 += 2) {
+        const int64_t jj[2] = {j0, j0 + 1 < n ? j0 + 1 : j0};
+        LosGeometry<float> G[2];
+        double ex[2], ey[2];
+        for (int q = 0; q < 2; ++q) {
+            const int64_t j = jj[q], jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+            G[q] = los_geometry<float>(u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo]);
+            ex[q] = earth[je];
+            ey[q] = earth[n_earth + je];
+        }
+        auto emit2 = [&](int ci, float a, float b) { out[ci * n + jj[0]] = a; out[ci * n + jj[1]] = b; };
+        if (K.share13) kelsall_group_a_x2<true>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2);
+        else kelsall_group_a_x2<false>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2);
+        if (K.n_comps == 6)
+            for (int q = 1; q >= 0; --q)
+                kelsall_ring_feature_packed(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask,
+                                            [&](float r, float f) { out[4 * n + jj[q]] = r; out[5 * n + jj[q]] = f; });
+    }
+}
+
+// fast: 0 generic routine, 1 scalar fused routine, 2 packed fused routines (fp32, no scattering).
 // Returns 1 if the Kelsall fast path was eligible and used, 0 if the generic routine ran.
 extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, int lanes, int fast,
                                       int64_t n, const double* u, const double* obs, int64_t n_obs,
@@ -102,6 +134,10 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
     if (precision == ZODI_FP32) {
         KelsallModel<float> k32;
         narrow_kelsall(k64, k32);
+        if (fast == 2 && !k32.scatter) {
+            run_kelsall_x2(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out);
+            return 2;
+        }
         run_kelsall<float>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
     } else {
         run_kelsall<double>(k64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);

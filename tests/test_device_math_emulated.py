@@ -32,7 +32,11 @@ def emu():
     return C.CDLL(LIB)
 
 
-def run_emu(emu, spec, u, obs, earth, precision, lanes):
+def run_emu(emu, spec, u, obs, earth, precision, lanes, fast=None):
+    """fast=None: generic routine; 1: scalar fused routine; 2: packed fused routines (when eligible).
+    Returns (emission, which routine ran)."""
+    if fast is not None:
+        return _run_emu_mode(emu, spec, u, obs, earth, precision, lanes, fast)
     desc, keep = pack_desc(spec)
     u, obs, earth = (np.ascontiguousarray(a, dtype=np.float64) for a in (u, obs, earth))
     flags = oracle.outside_flags(spec, obs)
@@ -43,6 +47,44 @@ def run_emu(emu, spec, u, obs, earth, precision, lanes):
                                ptr(flags), ptr(out))
     assert rc == 0
     return out
+
+
+def _run_emu_mode(emu, spec, u, obs, earth, precision, lanes, fast):
+    desc, keep = pack_desc(spec)
+    u, obs, earth = (np.ascontiguousarray(a, dtype=np.float64) for a in (u, obs, earth))
+    flags = oracle.outside_flags(spec, obs)
+    out = np.zeros((len(spec["comps"]), u.shape[1]))
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    used = emu.zodi_emu_evaluate_mode(C.byref(desc), precision, lanes, fast, C.c_int64(u.shape[1]), ptr(u),
+                                      ptr(obs), C.c_int64(obs.shape[1]), ptr(earth),
+                                      C.c_int64(earth.shape[1]), ptr(flags), ptr(out))
+    return out, used
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("case_id", case_ids())
+def test_fused_routines_match_reference(emu, case_id, precision):
+    """Scalar fused Kelsall routine (zodi_kelsall.cuh), fp64 and fp32."""
+    case, a = golden_case(case_id)
+    em, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], precision, 1, fast=1)
+    if not used:
+        pytest.skip("model layout takes the generic routine")
+    tol, floor = (TOL_FP64, COMP_FLOOR_FP64) if precision == 0 else (TOL_FP32, 1.0)
+    assert max_rel_total(em, a["emission"]) <= tol
+    assert max_rel_comps(em, a["emission"], floor=floor) <= tol
+
+
+@pytest.mark.parametrize("case_id", case_ids())
+def test_packed_routines_equal_scalar_fused(emu, case_id):
+    """Packed routines (zodi_kelsall_x2.cuh) perform the same operations as the scalar fused ones."""
+    case, a = golden_case(case_id)
+    packed, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=2)
+    if used != 2:
+        pytest.skip("not eligible for the packed routines (generic layout or scattering)")
+    scalar, _ = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=1)
+    # bit-identical on the GPU (ex2.approx.ftz flushes to 0); the host's libm returns denormals
+    # where one lane of a pair is beyond the underflow threshold, hence the 1e-37 allowance
+    np.testing.assert_allclose(packed, scalar, rtol=0, atol=1e-37)
 
 
 @pytest.mark.parametrize("case_id", case_ids())

@@ -251,8 +251,10 @@ template <bool HAS_RF, bool SHARE13>
 cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
                               const Pair<float>* nodes, cudaStream_t stream) {
     const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
-    // 5 CTAs/SM (48 registers): measured 5 % faster than 4 CTAs/SM (60 registers) on B200
-    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, 5><<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
+    // cloud+bands only: 5 CTAs/SM (48 registers) measured 5 % faster than 4 CTAs/SM (60 registers)
+    // on B200; with the ring/feature loops 48 registers spill, so that variant keeps 4 CTAs/SM.
+    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, HAS_RF ? 4 : 5>
+        <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

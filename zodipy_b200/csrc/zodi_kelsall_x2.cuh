@@ -44,6 +44,7 @@ ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v
 ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
 ZODI_HD F2 lg2_2(F2 v) { return f2(Math<float>::log2_(v.x), Math<float>::log2_(v.y)); }
 ZODI_HD F2 rsq_2(F2 v) { return f2(Math<float>::rsqrt_(v.x), Math<float>::rsqrt_(v.y)); }
+ZODI_HD F2 sqrt_2(F2 v) { return f2(Math<float>::sqrt_(v.x), Math<float>::sqrt_(v.y)); }
 
 // Table lookup for two temperatures (same arithmetic as table_at<float>).
 ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
@@ -144,6 +145,41 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     const F2 r0 = mul2(h, mul2(a0, K.aB[0])), r1 = mul2(h, mul2(a1, K.aB[1]));
     const F2 r2 = mul2(h, mul2(a2, K.aB[2])), r3 = mul2(h, mul2(a3, K.aB[3]));
     emit(0, r0.x, r0.y); emit(1, r1.x, r1.y); emit(2, r2.x, r2.y); emit(3, r3.x, r3.y);
+}
+
+// Ring and Feature of ONE line of sight in one packed loop: both components repeat the same
+// source-function work on their own quadrature nodes (own cutoff spheres), so the ring rides in
+// the low half and the feature in the high half of every register pair; only the feature's
+// longitude term (atan2) is scalar.  Same operations as kelsall_ring<float,false> /
+// kelsall_feature<float,false> (bit-identical results).  emit(ring_value, feature_value).
+template <typename Emit>
+ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pair<float>* tab,
+                                         const Pair<float>* nodes, const LosGeometry<float>& G,
+                                         double dex, double dey, uint32_t outside_mask, Emit emit) {
+    float hr, midr, hf, midf;
+    los_interval<float>(G, K.cutR_in, K.cutR_out, (outside_mask >> 8) & 1u, (outside_mask >> 9) & 1u, hr, midr);
+    los_interval<float>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, hf, midf);
+    const F2 h = f2(hr, hf), mid = f2(midr, midf);
+    const double th = atan2(dey, dex) + (double)K.f_theta0;  // see kelsall_feature()
+    const float cr = float(cos(th)), sr = float(sin(th));
+    const F2 R0 = f2(-K.r_R, -K.f_R), c2 = f2(K.r_c2, K.f_c2), c3 = f2(K.r_c3, K.f_c3);
+    const F2 nx = f2(K.rnx, K.fnx), ny = f2(K.rny, K.fny), nz = f2(K.rnz, K.fnz);
+    F2 acc = f2(0.f);
+    for (int k = 0; k < K.n_nodes; ++k) {
+        const Pair<float> nw = nodes[k];
+        const F2 R_los = fma2(h, nw.a, mid);
+        const F2 xh = fma2(R_los, G.ux, G.ox), yh = fma2(R_los, G.uy, G.oy), zh = fma2(R_los, G.uz, G.oz);
+        const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
+        const F2 t = fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs);
+        const F2 B = table_at2(tab, t, K.t_top);
+        const F2 d = add2(sqrt_2(Rh2), R0);
+        const F2 Zc = fma2(xh, nx, fma2(yh, ny, mul2(zh, nz)));
+        const float xr = fmaf(xh.y, cr, yh.y * sr), yr = fmaf(yh.y, cr, -(xh.y * sr));
+        const float dth = Math<float>::atan2_(yr, xr);
+        const F2 e = fma2(mul2(d, d), c2, fma2(f2(fabsf(Zc.x), fabsf(Zc.y)), c3, f2(0.f, dth * dth * K.f_c5)));
+        acc = fma2(mul2(B, nw.b), ex2_2(e), acc);
+    }
+    emit(hr * (K.aB[4] * acc.x), hf * (K.aB[5] * acc.y));
 }
 
 }  // namespace zodi

@@ -232,10 +232,13 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
     };
     kelsall_group_a_x2<SHARE13>(model, s_table, s_nodes, G[0], G[1], args.outside_mask, emit2);
     if (HAS_RF) {
-        emit2(4, kelsall_ring<float, false>(model, s_table, s_nodes, G[0], args.outside_mask, 0, 1),
-              kelsall_ring<float, false>(model, s_table, s_nodes, G[1], args.outside_mask, 0, 1));
-        emit2(5, kelsall_feature<float, false>(model, s_table, s_nodes, G[0], ex[0], ey[0], args.outside_mask, 0, 1),
-              kelsall_feature<float, false>(model, s_table, s_nodes, G[1], ex[1], ey[1], args.outside_mask, 0, 1));
+        float ring[2], feat[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            kelsall_ring_feature_packed(model, s_table, s_nodes, G[q], ex[q], ey[q], args.outside_mask,
+                                        [&](float r, float f) { ring[q] = r; feat[q] = f; });
+        emit2(4, ring[0], ring[1]);
+        emit2(5, feat[0], feat[1]);
     }
     if (!args.return_comps) {
         if (act0) store_out<float>(args, 0, j0, tot0);
