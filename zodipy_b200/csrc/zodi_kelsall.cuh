@@ -259,7 +259,7 @@ ZODI_HD Real kelsall_feature(const KelsallModel<Real>& K, const Pair<Real>* tab,
         const Real d = M::sqrt_(s.Rh2) - K.f_R;
         const Real Zc = M::fma_(s.xh, K.fnx, M::fma_(s.yh, K.fny, s.zh * K.fnz));
         const Real xr = M::fma_(s.xh, cr, s.yh * sr), yr = M::fma_(s.yh, cr, -(s.xh * sr));
-        const Real dth = M::atan2_(yr, xr);
+        const Real dth = M::atan2_abs_(yr, xr);  // only dth^2 is used
         const Real e = M::fma_(d * d, K.f_c2, M::fma_(M::abs_(Zc), K.f_c3, dth * dth * K.f_c5));
         const Real n = M::exp2_neg_(-e);
         aB = M::fma_(nw.b * s.B, n, aB);

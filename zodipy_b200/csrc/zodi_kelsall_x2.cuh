@@ -175,7 +175,7 @@ ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pai
         const F2 d = add2(sqrt_2(Rh2), R0);
         const F2 Zc = fma2(xh, nx, fma2(yh, ny, mul2(zh, nz)));
         const float xr = fmaf(xh.y, cr, yh.y * sr), yr = fmaf(yh.y, cr, -(xh.y * sr));
-        const float dth = Math<float>::atan2_(yr, xr);
+        const float dth = Math<float>::atan2_abs_(yr, xr);  // only dth^2 is used
         const F2 e = fma2(mul2(d, d), c2, fma2(f2(fabsf(Zc.x), fabsf(Zc.y)), c3, f2(0.f, dth * dth * K.f_c5)));
         acc = fma2(mul2(B, nw.b), ex2_2(e), acc);
     }
