@@ -35,6 +35,11 @@ UNIT = "evals/s"
 MODEL_NAME, X_GHZ, DEG = "planck18", 857.0, 50
 FLOPS_PER_UNIT = 60.25  # canonical algorithmic flops, Planck-type 4-comp mean
 SFU_PER_UNIT = 7.0
+# EXECUTED work of the packed fused kernel per evaluation, from the ncu capture committed as
+# profiles/r1_ncu_kelsall_x2_fp32_nside1024.md (per pair of lines of sight and node, / 8 evaluations):
+EXEC_ISSUE_PER_UNIT = 155.4 / 8   # warp-instruction issue slots
+EXEC_MUFU_PER_UNIT = 20.6 / 8     # XU-pipe instructions
+EXEC_FMA_CYCLES_PER_UNIT = 2 * 80.5 / 8  # FMA-pipe cycles (packed FFMA2/FMUL2/FADD2 take 2)
 EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])  # 2022-01-14, SURVEY.md 8(d)
 
 
@@ -380,6 +385,9 @@ def run_b200(args):
     peak_fp32 = engine.peak_probe("fp32", local_rank)
     peak_fp64 = engine.peak_probe("fp64", local_rank)
     peak_mufu = engine.peak_probe("mufu", local_rank)
+    props = torch.cuda.get_device_properties(dev)
+    sm_count = props.multi_processor_count
+    sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
     per_gpu_units = n_local * ncomps * DEG
     kernel_units_per_s = per_gpu_units / (kernel_ms * 1e-3)
     peak = peak_fp32 if precision == "fp32" else peak_fp64
@@ -387,13 +395,19 @@ def run_b200(args):
     roofline = {
         "bound": precision, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": None,
-        "kernel": dm.kernel_name, "kernel_ms": kernel_ms,
+        "kernel": dm.kernel_name_for(n_local, precision), "kernel_ms": kernel_ms,
         "flops_per_unit_canonical": FLOPS_PER_UNIT, "sfu_per_unit_canonical": SFU_PER_UNIT,
         "sfu_frac": kernel_units_per_s * SFU_PER_UNIT / peak_mufu,
         "peaks_measured": {"fp32_tflops": peak_fp32 / 1e12, "fp64_tflops": peak_fp64 / 1e12,
                            "mufu_tops": peak_mufu / 1e12,
                            "how": "zodi_peak_probe: FFMA / DFMA / MUFU.EX2 microbenchmarks, best of 5, "
                                   "same process, same GPU"},
+        "executed": None if (precision != "fp32" or "x2" not in dm.kernel_name_for(n_local, precision)) else {
+            # pipe utilisation implied by the measured rate and the executed counts of the ncu capture
+            "issue_slot_util": kernel_units_per_s * EXEC_ISSUE_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+            "xu_pipe_util": kernel_units_per_s * EXEC_MUFU_PER_UNIT / peak_mufu,
+            "fma_pipe_util": kernel_units_per_s * EXEC_FMA_CYCLES_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+            "counts_from": "profiles/r1_ncu_kelsall_x2_fp32_nside1024.md"},
         "algorithmic_hbm_bytes_per_los": 24 + (4 if precision == "fp32" else 8),
         "note": "compute-pipe bound (HBM traffic is 28-32 B per 200 evaluations); `peak` is the measured "
                 "pipe peak of the precision mode, not HBM/tensor",

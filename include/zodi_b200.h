@@ -189,6 +189,9 @@ int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);
 /* Name of the kernel family zodi_evaluate launches for this model: "zodi_los_kelsall_kernel"
  * (fused Kelsall-family kernel) or "zodi_los_generic_kernel" (any component list). */
 const char* zodi_model_kernel_name(zodi_model_t model);
+/* Exact kernel zodi_evaluate would launch for n lines of sight in the given precision
+ * ("zodi_los_kelsall_x2_kernel" = packed fp32 variant, ...). */
+const char* zodi_model_kernel_for(zodi_model_t model, int64_t n, int32_t precision);
 
 int zodi_evaluate_healpix(zodi_model_t model, const zodi_healpix_args* args);
 /* Pixel-centre unit vectors (3, n) of RING pixels [ipix_start, ipix_start + n) into device or host

@@ -91,6 +91,7 @@ SYMBOLS = {
     "zodi_model_update": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc)]),
     "zodi_model_destroy": (C.c_int, [C.c_void_p]),
     "zodi_model_kernel_name": (C.c_char_p, [C.c_void_p]),
+    "zodi_model_kernel_for": (C.c_char_p, [C.c_void_p, C.c_int64, C.c_int32]),
     "zodi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
     "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
     "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_double_p, C.c_void_p,

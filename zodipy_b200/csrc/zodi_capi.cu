@@ -679,6 +679,14 @@ int zodi_peer_buffer_free(int device, void* ptr) {
     return ZODI_OK;
 }
 
+const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
+    if (!m) return "";
+    if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";
+    if (precision == ZODI_FP32 && !m->k32.scatter && !m->no_x2 && pick_lanes(n / 2, m->k32.n_nodes) == 1)
+        return "zodi_los_kelsall_x2_kernel";
+    return "zodi_los_kelsall_kernel";
+}
+
 int64_t zodi_kernel_launch_count(void) { return g_launches.load(); }
 
 double zodi_last_kernel_ms(zodi_model_t m) { return m ? m->last_kernel_ms : 0.0; }

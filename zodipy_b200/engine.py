@@ -288,6 +288,10 @@ class DeviceModel:
     def kernel_name(self) -> str:
         return self._lib.zodi_model_kernel_name(self._handle).decode()
 
+    def kernel_name_for(self, n: int, precision: str = "fp64") -> str:
+        """The exact kernel an evaluation of ``n`` lines of sight would launch."""
+        return self._lib.zodi_model_kernel_for(self._handle, int(n), _PRECISIONS[precision]).decode()
+
     def last_kernel_ms(self) -> float:
         return float(self._lib.zodi_last_kernel_ms(self._handle))
 
