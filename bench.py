@@ -129,6 +129,21 @@ class ClockSampler:
         return out
 
 
+def tune_malloc_for_numpy():
+    """Keep glibc from mmap()/munmap()-ing every NumPy temporary (page-fault churn that made the
+    CPU path up to 1.5x slower in some allocator states, oracle/compare_speed_with_reference.py).
+    Inherited by the forked pool workers.  Only ever makes the CPU baseline FASTER."""
+    try:
+        import ctypes
+
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 1 << 30)  # M_MMAP_THRESHOLD
+        libc.mallopt(-1, 1 << 31)  # M_TRIM_THRESHOLD
+        libc.mallopt(-2, 1 << 28)  # M_TOP_PAD
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args):
     """CPU arm: the oracle port of the reference path driven like zodipy/model.py:182-198."""
@@ -140,6 +155,7 @@ def run_reference(args):
     import zodipy_b200 as zp
     from zodipy_b200 import healpix
 
+    tune_malloc_for_numpy()
     cores = os.cpu_count() or 1
     model = zp.Model(zp.Quantity(X_GHZ, "GHz"), name=MODEL_NAME, gauss_quad_degree=DEG)
     spec = model.spec
@@ -180,6 +196,7 @@ def cpu_baseline(spec, nside, budget_s=12.0):
     import zodi_oracle as oracle
     from zodipy_b200 import healpix
 
+    tune_malloc_for_numpy()
     cores = os.cpu_count() or 1
     npix = healpix.nside2npix(nside)
     rng = np.random.default_rng(0)

@@ -154,15 +154,18 @@ def los_range(spec, u, obs):
 # --------------------------------------------------------------------------------------
 def _plane_geometry(X, p):
     """Common prologue of every density (e.g. ``number_density.py:61-67``): offset position,
-    distance from the component centre and height above its symmetry plane."""
-    Xc = X - np.asarray(p["X_0"], dtype=np.float64).reshape(3, 1)
-    Rc = np.sqrt(Xc[0] ** 2 + Xc[1] ** 2 + Xc[2] ** 2)
+    distance from the component centre and height above its symmetry plane.  Row-wise to avoid
+    (3, N) temporaries (this port doubles as the CPU baseline and should not be slower than the
+    reference's own code); same operations in the same order as the reference."""
+    x0, y0, z0 = (float(v) for v in p["X_0"])
+    xc, yc, zc = X[0] - x0, X[1] - y0, X[2] - z0
+    Rc = np.sqrt(xc**2 + yc**2 + zc**2)
     Zc = (
-        Xc[0] * p["sin_Omega_rad"] * p["sin_i_rad"]
-        - Xc[1] * p["cos_Omega_rad"] * p["sin_i_rad"]
-        + Xc[2] * p["cos_i_rad"]
+        xc * p["sin_Omega_rad"] * p["sin_i_rad"]
+        - yc * p["cos_Omega_rad"] * p["sin_i_rad"]
+        + zc * p["cos_i_rad"]
     )
-    return Xc, Rc, Zc
+    return (xc, yc, zc), Rc, Zc
 
 
 def density_cloud(X, p, earth=None):  # number_density.py:47-73
