@@ -29,7 +29,7 @@ EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])
 def healpix_dirs(nside, dev):
     u = torch.empty((3, 12 * nside * nside), dtype=torch.float64, device=dev)
     _cabi = engine._cabi
-    _cabi.check(_cabi.load().zodi_healpix_vectors(dev.index, nside, 0, u.shape[1], None, u.data_ptr(),
+    _cabi.check(_cabi.load().zodi_healpix_vectors(dev.index, nside, 0, 0, u.shape[1], None, u.data_ptr(),
                                                   u.shape[1], _cabi.MEM_DEVICE, None))
     torch.cuda.synchronize()
     return u

@@ -158,7 +158,7 @@ typedef struct {
 } zodi_eval_args;
 
 /* HEALPix map evaluation with directions generated on the device (no (3, N) upload):
- * line of sight j of the call is the centre of RING pixel ipix_start + j of resolution nside,
+ * line of sight j of the call is the centre of pixel ipix_start + j (RING or NESTED) of resolution nside,
  * optionally rotated by `rot` (row-major 3x3: pixel frame -> mean ecliptic, i.e. the constant
  * matrix behind skycoord.transform_to(BarycentricMeanEcliptic), zodipy/model.py:247).
  * `base.u`/`base.u_stride` are ignored; everything else in `base` keeps its meaning
@@ -168,7 +168,7 @@ typedef struct {
     zodi_eval_args base;
     int64_t nside;
     int64_t ipix_start;
-    int32_t nest;      /* 0 = RING (supported); 1 = NESTED (ZODI_ERR_UNSUPPORTED for now) */
+    int32_t nest;      /* 0 = RING, 1 = NESTED (nside must then be a power of two) */
     int32_t has_rot;
     double rot[9];
 } zodi_healpix_args;
@@ -194,10 +194,11 @@ const char* zodi_model_kernel_name(zodi_model_t model);
 const char* zodi_model_kernel_for(zodi_model_t model, int64_t n, int32_t precision);
 
 int zodi_evaluate_healpix(zodi_model_t model, const zodi_healpix_args* args);
-/* Pixel-centre unit vectors (3, n) of RING pixels [ipix_start, ipix_start + n) into device or host
- * memory (`memory`), rotated by rot if non-NULL: the directions zodi_evaluate_healpix integrates. */
-int zodi_healpix_vectors(int device, int64_t nside, int64_t ipix_start, int64_t n, const double* rot,
-                         double* out, int64_t out_stride, int32_t memory, void* stream);
+/* Pixel-centre unit vectors (3, n) of pixels [ipix_start, ipix_start + n) (RING or NESTED) into
+ * device or host memory (`memory`), rotated by rot if non-NULL: the directions
+ * zodi_evaluate_healpix integrates. */
+int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_start, int64_t n,
+                         const double* rot, double* out, int64_t out_stride, int32_t memory, void* stream);
 
 /* Largest heliocentric observer distance sqrt(x^2+y^2+z^2) over (3, n_obs) observers and the
  * resulting early-out flags; used to form the GLOBAL flags when a job is sharded over GPUs

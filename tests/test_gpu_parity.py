@@ -208,6 +208,13 @@ def test_healpix_vectors_match_host_pix2vec():
     for rng in ((0, 5000), (npix - 5000, npix)):
         np.testing.assert_allclose(engine.healpix_vectors(nside, rng),
                                    healpix.pix2vec_ring(nside, np.arange(*rng)), rtol=0, atol=3e-16)
+    for nside in (1, 2, 64, 2048):  # NESTED ordering
+        npix = healpix.nside2npix(nside)
+        rng = (0, npix) if npix <= 49152 else (npix // 3, npix // 3 + 5000)
+        np.testing.assert_allclose(engine.healpix_vectors(nside, rng, nest=True),
+                                   healpix.pix2vec_nest(nside, np.arange(*rng)), rtol=0, atol=3e-16)
+    with pytest.raises(engine._cabi.ZodiError):
+        engine.healpix_vectors(12, nest=True)  # NESTED needs a power of two
     c, s_ = np.cos(0.4), np.sin(0.4)
     rot = np.array([[1, 0, 0], [0, c, s_], [0, -s_, c]])
     np.testing.assert_allclose(engine.healpix_vectors(16, rot=rot),
@@ -243,6 +250,8 @@ def test_evaluate_healpix_equals_array_seam(precision):
     sel = np.arange(0, u.shape[1], 97)
     ref_o = oracle.evaluate(model.spec, u[:, sel], EARTH_20220114, EARTH_20220114)
     assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
+    nested = model.evaluate_healpix(nside, EARTH_20220114, nest=True)
+    np.testing.assert_allclose(nested, ref.sum(axis=0)[healpix.nest2ring(nside, np.arange(u.shape[1]))], rtol=tol)
     with pytest.raises(ValueError):
         model.evaluate_healpix(4, EARTH_20220114, pix_range=(0, 12 * 16 + 1))
     assert model.evaluate_healpix(4, EARTH_20220114, pix_range=(7, 7)).shape == (0,)

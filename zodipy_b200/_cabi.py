@@ -94,7 +94,7 @@ SYMBOLS = {
     "zodi_model_kernel_for": (C.c_char_p, [C.c_void_p, C.c_int64, C.c_int32]),
     "zodi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
     "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
-    "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
+    "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
                                        C.c_int64, C.c_int32, C.c_void_p]),
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),

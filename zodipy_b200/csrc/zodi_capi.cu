@@ -348,12 +348,13 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
 
 void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
     la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0;
-    la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0;
+    la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0; la.hp_nest = 0;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = 0.0;
     if (!hp) return;
     la.hp_nside = hp->nside;
     la.hp_start = hp->ipix_start + offset;
     la.hp_rotate = hp->has_rot != 0;
+    la.hp_nest = hp->nest != 0;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = hp->rot[i];
 }
 
@@ -572,7 +573,8 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
 int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) { return evaluate_impl(m, a, nullptr); }
 
 static int check_healpix(int64_t nside, int64_t ipix_start, int64_t n, int nest) {
-    if (nest) return fail(ZODI_ERR_UNSUPPORTED, "NESTED pixel ordering is not implemented yet");
+    if (nest && (nside & (nside - 1)) != 0)
+        return fail(ZODI_ERR_INVALID, "NESTED ordering needs nside to be a power of two (got %lld)", (long long)nside);
     if (nside < 1 || nside > (1ll << 29)) return fail(ZODI_ERR_INVALID, "nside=%lld out of range", (long long)nside);
     const int64_t npix = 12 * nside * nside;
     if (ipix_start < 0 || n < 0 || ipix_start + n > npix)
@@ -596,9 +598,9 @@ int zodi_evaluate_healpix(zodi_model_t m, const zodi_healpix_args* hp) {
     return evaluate_impl(m, &hp->base, hp);
 }
 
-int zodi_healpix_vectors(int device, int64_t nside, int64_t ipix_start, int64_t n, const double* rot,
-                         double* out, int64_t out_stride, int32_t memory, void* stream) {
-    int rc = check_healpix(nside, ipix_start, n, 0);
+int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_start, int64_t n,
+                         const double* rot, double* out, int64_t out_stride, int32_t memory, void* stream) {
+    int rc = check_healpix(nside, ipix_start, n, nest);
     if (rc) return rc;
     if (!out || out_stride < n) return fail(ZODI_ERR_INVALID, "bad output buffer");
     if (n == 0) return ZODI_OK;
@@ -609,7 +611,7 @@ int zodi_healpix_vectors(int device, int64_t nside, int64_t ipix_start, int64_t 
     la.n = n;
     zodi_healpix_args hp;
     std::memset(&hp, 0, sizeof(hp));
-    hp.nside = nside; hp.ipix_start = ipix_start; hp.has_rot = rot != nullptr;
+    hp.nside = nside; hp.ipix_start = ipix_start; hp.has_rot = rot != nullptr; hp.nest = nest;
     if (rot) std::memcpy(hp.rot, rot, sizeof(hp.rot));
     set_healpix(la, &hp, 0);
     cudaStream_t st = (cudaStream_t)stream;

@@ -34,6 +34,7 @@ struct LaunchArgs {
     int64_t peer_offset;  int64_t peer_stride;
     // on-device directions: HEALPix RING pixel hp_start + j (u is ignored when hp_nside > 0)
     int64_t hp_nside;     int64_t hp_start;
+    int hp_nest;          // 1: hp_start + j is a NESTED index (converted to RING on the fly)
     int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel vector
     // block-cyclic shard layout (see zodi_eval_args.cyclic_block); 0 = identity
     int64_t cyc_block;    int cyc_parts;      int cyc_rank;
@@ -51,7 +52,9 @@ __device__ __forceinline__ void load_direction(const LaunchArgs& a, int64_t jj, 
                                                double& uz) {
     if (a.hp_nside > 0) {
         double x, y, z;
-        healpix_ring_pix2vec(a.hp_nside, a.hp_start + global_index(a, jj), x, y, z);
+        long long ipix = a.hp_start + global_index(a, jj);
+        if (a.hp_nest) ipix = healpix_nest2ring(a.hp_nside, ipix);
+        healpix_ring_pix2vec(a.hp_nside, ipix, x, y, z);
         if (a.hp_rotate) {
             ux = a.hp_rot[0] * x + a.hp_rot[1] * y + a.hp_rot[2] * z;
             uy = a.hp_rot[3] * x + a.hp_rot[4] * y + a.hp_rot[5] * z;

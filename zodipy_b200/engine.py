@@ -194,12 +194,13 @@ class DeviceModel:
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 
-    def evaluate_healpix(self, nside: int, obs, earth=None, *, pix_range=None, rot=None,
+    def evaluate_healpix(self, nside: int, obs, earth=None, *, pix_range=None, rot=None, nest: bool = False,
                          return_comps: bool = False, precision: str = "fp64", out=None,
                          out_dtype=None, device_out: bool = False, peer_map=None):
         """Emission for HEALPix RING pixels with the directions generated ON THE DEVICE.
 
-        Line of sight j is the centre of pixel ``pix_range[0] + j`` (default: the whole map),
+        Line of sight j is the centre of pixel ``pix_range[0] + j`` (default: the whole map; RING order
+        unless ``nest``),
         rotated by the optional 3x3 ``rot`` (pixel frame -> mean ecliptic).  ``obs`` / ``earth``
         are single positions (3,) [AU] (instantaneous map).  Nothing but these few numbers is
         uploaded; the result is returned as a NumPy array (host; D2H pipelined inside the
@@ -274,7 +275,7 @@ class DeviceModel:
             a.peer_offset, a.peer_stride = peer_map.offset, peer_map.n_total
             if peer_map.cyclic is not None:
                 a.cyclic_block, a.cyclic_parts, a.cyclic_rank = peer_map.cyclic
-        h.nside, h.ipix_start, h.nest = nside, lo, 0
+        h.nside, h.ipix_start, h.nest = nside, lo, int(bool(nest))
         if rot is not None:
             r = np.asarray(rot, dtype=np.float64).reshape(9)
             h.has_rot = 1
@@ -300,8 +301,8 @@ def kernel_launch_count() -> int:
     return int(_cabi.load().zodi_kernel_launch_count())
 
 
-def healpix_vectors(nside: int, pix_range=None, rot=None, device: int = 0) -> np.ndarray:
-    """(3, n) RING pixel-centre unit vectors computed by the device routine (host array)."""
+def healpix_vectors(nside: int, pix_range=None, rot=None, device: int = 0, nest: bool = False) -> np.ndarray:
+    """(3, n) pixel-centre unit vectors (RING or NESTED) computed by the device routine (host array)."""
     nside = int(nside)
     lo, hi = (0, 12 * nside * nside) if pix_range is None else (int(pix_range[0]), int(pix_range[1]))
     out = np.empty((3, hi - lo), dtype=np.float64)
@@ -309,7 +310,7 @@ def healpix_vectors(nside: int, pix_range=None, rot=None, device: int = 0) -> np
     if rot is not None:
         rot_a = np.ascontiguousarray(np.asarray(rot, dtype=np.float64).reshape(9))
         rot_p = _cabi.as_double_p(rot_a)
-    _cabi.check(_cabi.load().zodi_healpix_vectors(int(device), nside, lo, hi - lo, rot_p, out.ctypes.data,
+    _cabi.check(_cabi.load().zodi_healpix_vectors(int(device), nside, int(bool(nest)), lo, hi - lo, rot_p, out.ctypes.data,
                                                   max(hi - lo, 1), _cabi.MEM_HOST, None))
     return out
 

@@ -76,3 +76,45 @@ def full_sky_vectors(nside: int, start: int = 0, stop: int | None = None, chunk:
         hi = min(n, lo + chunk)
         out[:, lo:hi] = pix2vec_ring(nside, np.arange(start + lo, start + hi, dtype=np.int64))
     return out
+
+
+# ---- NESTED scheme --------------------------------------------------------------------------
+_JRLL = np.array([2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4], dtype=np.int64)
+_JPLL = np.array([1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7], dtype=np.int64)
+
+
+def _compact_bits(v):
+    """De-interleave: keep the even-position bits of v (x index of a Morton code)."""
+    v = v & 0x5555555555555555
+    v = (v | (v >> 1)) & 0x3333333333333333
+    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0F
+    v = (v | (v >> 4)) & 0x00FF00FF00FF00FF
+    v = (v | (v >> 8)) & 0x0000FFFF0000FFFF
+    v = (v | (v >> 16)) & 0x00000000FFFFFFFF
+    return v
+
+
+def nest2ring(nside: int, ipix) -> np.ndarray:
+    """NESTED -> RING pixel index (nside must be a power of two)."""
+    if nside & (nside - 1):
+        raise ValueError("NESTED ordering needs nside to be a power of two")
+    ipix = np.asarray(ipix, dtype=np.int64)
+    npface = nside * nside
+    face = ipix // npface
+    ipf = ipix & (npface - 1)
+    ix, iy = _compact_bits(ipf), _compact_bits(ipf >> 1)
+    jr = _JRLL[face] * nside - ix - iy - 1  # ring number in 1 .. 4 nside - 1
+    nr = np.where(jr < nside, jr, np.where(jr > 3 * nside, 4 * nside - jr, nside))
+    n_before = np.where(jr < nside, 2 * nr * (nr - 1),
+                        np.where(jr > 3 * nside, 12 * npface - 2 * (nr + 1) * nr,
+                                 2 * nside * (nside - 1) + (jr - nside) * 4 * nside))
+    kshift = np.where((jr < nside) | (jr > 3 * nside), 0, (jr - nside) & 1)
+    jp = (_JPLL[face] * nr + ix - iy + 1 + kshift) // 2
+    jp = np.where(jp > 4 * nr, jp - 4 * nr, jp)
+    jp = np.where(jp < 1, jp + 4 * nr, jp)
+    return n_before + jp - 1
+
+
+def pix2vec_nest(nside: int, ipix) -> np.ndarray:
+    """Unit vectors (3, n) of NESTED-ordered pixel centres."""
+    return pix2vec_ring(nside, nest2ring(nside, ipix))

@@ -107,9 +107,9 @@ class Model:
             outside_flags=outside_flags)
 
     def evaluate_healpix(self, nside: int, obs_xyz, earth_xyz=None, *, frame_rotation=None,
-                         pix_range=None, return_comps: bool = False, precision: str | None = None,
-                         out=None, out_dtype=None, device_out: bool = False):
-        """Full-sky (or ``pix_range``) HEALPix RING map for one observation time, with the pixel
+                         pix_range=None, nest: bool = False, return_comps: bool = False,
+                         precision: str | None = None, out=None, out_dtype=None, device_out: bool = False):
+        """Full-sky (or ``pix_range``) HEALPix map (RING, or NESTED with ``nest=True``) for one observation time, with the pixel
         directions generated on the GPU (additive entry).
 
         Equivalent to ``evaluate_xyz(R @ pix2vec(nside, ipix), obs_xyz, earth_xyz)`` - what the
@@ -118,7 +118,7 @@ class Model:
         matrix taking pixel-frame vectors to mean-ecliptic ones (identity if the map is ecliptic).
         """
         return self.device_model.evaluate_healpix(
-            nside, obs_xyz, earth_xyz, pix_range=pix_range, rot=frame_rotation,
+            nside, obs_xyz, earth_xyz, pix_range=pix_range, rot=frame_rotation, nest=nest,
             return_comps=return_comps, precision=precision or self._precision, out=out,
             out_dtype=out_dtype, device_out=device_out)
 
