@@ -108,6 +108,7 @@ typedef struct {
 } zodi_model_desc;
 
 typedef struct zodi_model_s* zodi_model_t;
+typedef struct zodi_ephemeris_s* zodi_ephemeris_t; /* device-resident ephemeris spline, see below */
 
 /* Arguments of one evaluation = the arrays at the seam zodipy/model.py:253-279.
  * Layout is the reference's: structure-of-arrays, row k of a (3, n) array starts at
@@ -155,7 +156,25 @@ typedef struct {
     int64_t cyclic_block;
     int32_t cyclic_parts;
     int32_t cyclic_rank;
+    /* On-device ephemeris: when `ephemeris` is non-NULL, obs / earth (and their n_*, strides) are
+     * ignored and sample j uses the spline positions at obstime[j] (obstime: n doubles, same
+     * memory kind as u).  outside_flags must then be supplied (see zodi_ephemeris_stats). */
+    zodi_ephemeris_t ephemeris;
+    const double* obstime;
 } zodi_eval_args;
+
+/* Time-ordered data with Earth / observer positions evaluated ON THE DEVICE from a cubic spline
+ * through uniformly spaced ephemeris knots.  Replaces get_interp_bodypos (zodipy/bodies.py:22-35:
+ * hourly knots from arrange_obstimes :16-19 + scipy.interpolate.CubicSpline, default not-a-knot
+ * ends, evaluated at every sample) and the SEMB-L2 scaling (:38-50), and removes the 48 B per
+ * sample of position arrays from the host -> device traffic. */
+typedef struct {
+    int64_t n_knots;           /* >= 4 */
+    double t0, dt;             /* knot k is at time t0 + k * dt (same unit as the obstime array) */
+    const double* earth_knots; /* (3, n_knots) row-major, host: Earth position at the knots [AU] */
+    const double* obs_knots;   /* (3, n_knots) host, or NULL: observer = obs_scale * Earth */
+    double obs_scale;          /* 1 for obspos="earth"; 1 + L2 / ||earth|| for "semb-l2" */
+} zodi_ephemeris_desc;
 
 /* HEALPix map evaluation with directions generated on the device (no (3, N) upload):
  * line of sight j of the call is the centre of pixel ipix_start + j (RING or NESTED) of resolution nside,
@@ -182,6 +201,22 @@ int zodi_device_count(int* count);
 int zodi_model_create(const zodi_model_desc* desc, int device, zodi_model_t* out);
 int zodi_model_update(zodi_model_t model, const zodi_model_desc* desc); /* Model.update_parameters */
 int zodi_model_destroy(zodi_model_t model);
+
+/* ---- on-device ephemeris (time-ordered data) ------------------------------------------------- */
+int zodi_ephemeris_create(int device, const zodi_ephemeris_desc* desc, zodi_ephemeris_t* out);
+int zodi_ephemeris_set_obs_scale(zodi_ephemeris_t eph, double obs_scale);
+int zodi_ephemeris_destroy(zodi_ephemeris_t eph);
+/* Piecewise-cubic coefficients of the Earth spline as scipy's CubicSpline.c lays them out:
+ * c[(k * (n_knots - 1) + i) * 3 + axis], k = 0..3 (highest power first); host output, for tests. */
+int zodi_ephemeris_coefficients(zodi_ephemeris_t eph, double* c);
+/* Spline positions at n times: earth_out / obs_out (3, n) row-major (either may be NULL). */
+int zodi_ephemeris_positions(zodi_ephemeris_t eph, const double* t, int64_t n, int32_t memory,
+                             double* earth_out, double* obs_out, void* stream);
+/* Reductions over the samples needed by the reference's semantics: sum of |earth|^2 (the
+ * un-axised np.linalg.norm of get_semb_l2_pos, bodies.py:47), max |earth|^2 and
+ * max |observer|^2 (the global early-out flags, line_of_sight.py:72-73).  stats = 3 doubles (host). */
+int zodi_ephemeris_stats(zodi_ephemeris_t eph, const double* t, int64_t n, int32_t memory, void* stream,
+                         double* stats);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);

@@ -144,3 +144,15 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
     }
     return 1;
 }
+
+// Not-a-knot cubic spline coefficients (the routine zodi_ephemeris_create uses), scipy layout
+// c[k * (n - 1) + i], k = 0..3 highest power first.
+extern "C" int zodi_emu_spline(int n, const double* x, const double* y, double* c) {
+    std::vector<double> xs(x, x + n), c0, c1, c2, c3;
+    cubic_spline_not_a_knot(xs, y, c0, c1, c2, c3);
+    for (int i = 0; i < n - 1; ++i) {
+        c[0 * (n - 1) + i] = c0[i]; c[1 * (n - 1) + i] = c1[i];
+        c[2 * (n - 1) + i] = c2[i]; c[3 * (n - 1) + i] = c3[i];
+    }
+    return 0;
+}

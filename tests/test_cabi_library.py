@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes(lib):
     # sizes computed from the header's field lists (8-byte alignment throughout)
     assert C.sizeof(_cabi.ComponentDesc) == 8 + 3 * 8 + 4 * 8 + 8 * 8 + 2 * 8 + 2 * 8 + 2 * 8
     assert C.sizeof(_cabi.ModelDesc) == 6 * 4 + 7 * 8 + 4 * 8 + 16 * C.sizeof(_cabi.ComponentDesc)
-    assert C.sizeof(_cabi.EvalArgs) == 8 + 16 + 24 + 24 + 8 + 16 + 16 + 8 + 8 + 8 * 8 + 16 + 16
+    assert C.sizeof(_cabi.EvalArgs) == 8 + 16 + 24 + 24 + 8 + 16 + 16 + 8 + 8 + 8 * 8 + 16 + 16 + 16
     assert lib.zodi_abi_version() == _cabi.ABI_VERSION
 
 

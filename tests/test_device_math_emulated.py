@@ -110,3 +110,21 @@ def test_fp32_arithmetic_within_tolerance(emu, case_id):
     em = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1)
     assert max_rel_total(em, a["emission"]) <= TOL_FP32
     assert max_rel_comps(em, a["emission"], floor=1.0) <= TOL_FP32
+
+
+@pytest.mark.parametrize("n", [4, 5, 25, 200])
+def test_spline_builder_matches_scipy(emu, n):
+    """The library's not-a-knot spline (ephemeris interpolation, zodipy/bodies.py:29-35) against
+    scipy.interpolate.CubicSpline, uniform and non-uniform knots."""
+    from scipy.interpolate import CubicSpline
+
+    rng = np.random.default_rng(n)
+    for x in (59215.0 + np.arange(n) / 24.0, np.sort(rng.uniform(0, 10, n))):
+        y = np.cos(0.7 * (x - x[0])) + 0.1 * rng.standard_normal(n)
+        c = np.zeros((4, n - 1))
+        x_c, y_c = np.ascontiguousarray(x), np.ascontiguousarray(y)
+        emu.zodi_emu_spline(n, x_c.ctypes.data_as(C.c_void_p), y_c.ctypes.data_as(C.c_void_p),
+                            c.ctypes.data_as(C.c_void_p))
+        ref = CubicSpline(x, y).c
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert np.max(np.abs(c - ref) / scale) < 1e-11

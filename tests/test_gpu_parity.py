@@ -280,3 +280,76 @@ def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
     ref = oracle.evaluate(model.spec, u[:, sel], obs[:, sel], EARTH_20220114)
     assert max_rel_total(a[:, sel], ref) <= TOL_FP32
     assert max_rel_comps(a[:, sel], ref, floor=COMP_FLOOR_FP32) <= TOL_FP32
+
+
+def _tod_inputs(n, seed=0):
+    """Hourly Earth knots over ~40 days (analytic orbit), random sample times and pointings."""
+    rng = np.random.default_rng(seed)
+    t0, dt, n_knots = 59215.0, 1.0 / 24.0, 40 * 24 + 1
+    tk = t0 + dt * np.arange(n_knots)
+    lon = 2 * np.pi * (tk - t0) / 365.25 + 1.7
+    r = 1.0 - 0.0167 * np.cos(lon - 1.8)
+    earth_knots = np.array([r * np.cos(lon), r * np.sin(lon), 1e-5 * np.sin(3 * lon)])
+    t = np.sort(rng.uniform(t0, tk[-1], n))
+    u = rng.normal(size=(3, n))
+    u /= np.linalg.norm(u, axis=0)
+    return t0, dt, earth_knots, tk, t, np.ascontiguousarray(u)
+
+
+def test_device_ephemeris_matches_scipy_cubic_spline():
+    from scipy.interpolate import CubicSpline
+
+    t0, dt, earth_knots, tk, t, _ = _tod_inputs(5000)
+    eph = engine.DeviceEphemeris(t0, dt, earth_knots)
+    spline = CubicSpline(tk, earth_knots, axis=-1)  # bodies.py:34
+    c_ref = spline.c  # (4, n-1, 3)
+    c = eph.coefficients()
+    assert np.max(np.abs(c - c_ref) / np.abs(c_ref).max(axis=(1, 2), keepdims=True)) < 1e-11
+    earth, obs = eph.positions(t)
+    np.testing.assert_allclose(earth, spline(t), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(obs, earth, rtol=0, atol=0)  # default observer = Earth
+    sum_r2, max_e, max_o = eph.stats(t)
+    ref = spline(t)
+    assert sum_r2 == pytest.approx((ref**2).sum(), rel=1e-13)
+    assert max_e == pytest.approx(np.sqrt((ref**2).sum(axis=0)).max(), rel=1e-14)
+    # observer knots (e.g. another body): own spline
+    obs_knots = earth_knots * 1.3 + 0.01
+    eph2 = engine.DeviceEphemeris(t0, dt, earth_knots, obs_knots)
+    _, obs2 = eph2.positions(t)
+    np.testing.assert_allclose(obs2, CubicSpline(tk, obs_knots, axis=-1)(t), rtol=0, atol=3e-15)
+    assert eph2.prepare(t, "knots") == pytest.approx(np.sqrt((obs2**2).sum(axis=0)).max(), rel=1e-14)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("observer", ["earth", "semb-l2", "knots"])
+def test_evaluate_tod_on_device_equals_host_interpolation(observer, precision):
+    """On-device ephemeris == the reference's host interpolation (scipy CubicSpline per sample,
+    get_semb_l2_pos incl. its whole-array norm) fed through the array seam; host and device memory."""
+    import torch
+    from scipy.interpolate import CubicSpline
+
+    n = 20000
+    t0, dt, earth_knots, tk, t, u = _tod_inputs(n, seed=3)
+    earth = CubicSpline(tk, earth_knots, axis=-1)(t)  # bodies.py:22-35
+    obs_knots = None
+    if observer == "earth":
+        obs = earth
+    elif observer == "semb-l2":  # bodies.py:38-50 (np.linalg.norm over the whole (3, N) array)
+        norm = np.linalg.norm(earth)
+        obs = earth / norm * (norm + engine.MEAN_DIST_TO_L2)
+    else:
+        obs_knots = earth_knots * 1.01 + np.array([[0.0], [0.0], [0.002]])
+        obs = CubicSpline(tk, obs_knots, axis=-1)(t)
+    model = zp.Model(zp.Quantity(25.0, "um"), precision=precision)
+    eph = engine.DeviceEphemeris(t0, dt, earth_knots, obs_knots)
+    ref = model.evaluate_xyz(u, obs, earth, return_comps=True)
+    got = model.evaluate_tod_xyz(u, t, eph, observer=observer, return_comps=True)
+    tol = 1e-11 if precision == "fp64" else 3e-6
+    np.testing.assert_allclose(got, ref, rtol=tol, atol=1e-30)
+    dev = torch.device("cuda:0")
+    got_dev = model.evaluate_tod_xyz(torch.as_tensor(u, device=dev), torch.as_tensor(t, device=dev), eph,
+                                     observer=observer, return_comps=True)
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), got)
+    sel = np.arange(0, n, 40)
+    ref_o = oracle.evaluate(model.spec, u[:, sel], obs[:, sel], earth[:, sel])
+    assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]

@@ -70,6 +70,14 @@ class EvalArgs(C.Structure):
         ("peer_out", C.c_void_p * MAX_PEERS),
         ("peer_offset", C.c_int64), ("peer_stride", C.c_int64),
         ("cyclic_block", C.c_int64), ("cyclic_parts", C.c_int32), ("cyclic_rank", C.c_int32),
+        ("ephemeris", C.c_void_p), ("obstime", C.c_void_p),
+    ]
+
+
+class EphemerisDesc(C.Structure):
+    _fields_ = [
+        ("n_knots", C.c_int64), ("t0", C.c_double), ("dt", C.c_double),
+        ("earth_knots", c_double_p), ("obs_knots", c_double_p), ("obs_scale", C.c_double),
     ]
 
 
@@ -93,6 +101,13 @@ SYMBOLS = {
     "zodi_model_kernel_name": (C.c_char_p, [C.c_void_p]),
     "zodi_model_kernel_for": (C.c_char_p, [C.c_void_p, C.c_int64, C.c_int32]),
     "zodi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
+    "zodi_ephemeris_create": (C.c_int, [C.c_int, C.POINTER(EphemerisDesc), C.POINTER(C.c_void_p)]),
+    "zodi_ephemeris_set_obs_scale": (C.c_int, [C.c_void_p, C.c_double]),
+    "zodi_ephemeris_destroy": (C.c_int, [C.c_void_p]),
+    "zodi_ephemeris_coefficients": (C.c_int, [C.c_void_p, c_double_p]),
+    "zodi_ephemeris_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "zodi_ephemeris_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, c_double_p]),
     "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
     "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
                                        C.c_int64, C.c_int32, C.c_void_p]),

@@ -87,6 +87,16 @@ struct zodi_model_s {
     double last_kernel_ms = 0.0;
 };
 
+struct zodi_ephemeris_s {
+    int device = 0;
+    int64_t n_knots = 0;
+    double t0 = 0.0, dt = 1.0, obs_scale = 1.0;
+    std::vector<double> earth_c;  // host copy, device layout [seg][axis][4]
+    double* d_earth = nullptr;
+    double* d_obs = nullptr;      // NULL: observer = obs_scale * Earth
+    double* d_stats = nullptr;    // 3 doubles: sum, max bits x2
+};
+
 namespace {
 
 int validate_desc(const zodi_model_desc* d) {
@@ -325,6 +335,15 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
                                    a->peer_stride < a->peer_offset + a->n))
             return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
     }
+    if (a->ephemeris) {
+        if (!a->obstime) return fail(ZODI_ERR_INVALID, "obstime must be non-NULL with an ephemeris");
+        if (!a->outside_flags)
+            return fail(ZODI_ERR_INVALID, "outside_flags must be supplied with an ephemeris (zodi_ephemeris_stats)");
+        if (a->ephemeris->device != m->device) return fail(ZODI_ERR_INVALID, "ephemeris lives on another device");
+        if ((need_u && !a->u) || (!a->out && a->n_peers == 0)) return fail(ZODI_ERR_INVALID, "u/out must be non-NULL");
+        if (need_u && a->u_stride < a->n) return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
+        goto positions_checked;
+    }
     if ((need_u && !a->u) || !a->obs || !a->earth || (!a->out && a->n_peers == 0))
         return fail(ZODI_ERR_INVALID, "u/obs/earth/out must be non-NULL");
     if (a->n_obs != 1 && a->n_obs != a->n)
@@ -335,6 +354,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
                     (long long)a->n);
     if ((need_u && a->u_stride < a->n) || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
         return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
+positions_checked:
     if (a->return_comps && a->n_peers == 0 && a->out_stride < a->n)
         return fail(ZODI_ERR_INVALID, "out_stride=%lld < n", (long long)a->out_stride);
     if (a->precision != ZODI_FP64 && a->precision != ZODI_FP32)
@@ -346,8 +366,17 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
     return ZODI_OK;
 }
 
+void set_ephemeris(LaunchArgs& la, const zodi_ephemeris_s* e, const double* obstime) {
+    la.eph_coef = nullptr; la.eph_obs_coef = nullptr; la.obstime = nullptr;
+    la.eph_nseg = 0; la.eph_t0 = 0.0; la.eph_dt = 1.0; la.eph_scale = 1.0;
+    if (!e) return;
+    la.eph_coef = e->d_earth; la.eph_obs_coef = e->d_obs; la.obstime = obstime;
+    la.eph_nseg = e->n_knots - 1; la.eph_t0 = e->t0; la.eph_dt = e->dt; la.eph_scale = e->obs_scale;
+}
+
 void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
     la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0;
+    set_ephemeris(la, nullptr, nullptr);
     la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0; la.hp_nest = 0;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = 0.0;
     if (!hp) return;
@@ -383,7 +412,8 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
     chunk = std::min<int64_t>(m->ws_chunk, std::max<int64_t>(chunk, 1));
     const size_t osz = a->out_dtype == ZODI_OUT_F32 ? sizeof(float) : sizeof(double);
     const int out_rows = a->return_comps ? m->desc.n_comps : 1;
-    const bool obs_ps = a->n_obs == n && n > 1, earth_ps = a->n_earth == n && n > 1;
+    const bool obs_ps = !a->ephemeris && a->n_obs == n && n > 1;
+    const bool earth_ps = !a->ephemeris && a->n_earth == n && n > 1;
     for (Slot& s : m->slots) s.used = false;
 
     // single observer / Earth: upload once into slot-independent spots (tail of slot 0 input)
@@ -400,11 +430,15 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         if (!hp)
             CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
                                        (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
+        if (a->ephemeris)  // obstime only (8 B per sample instead of 48 B of positions)
+            CU_CHECK(cudaMemcpyAsync(d_obs, a->obstime + done, (size_t)cn * sizeof(double),
+                                     cudaMemcpyHostToDevice, s.stream));
+        else
         CU_CHECK(cudaMemcpy2DAsync(d_obs, pitch, a->obs + (obs_ps ? done : 0),
                                    (size_t)a->obs_stride * sizeof(double),
                                    (size_t)(obs_ps ? cn : 1) * sizeof(double), 3,
                                    cudaMemcpyHostToDevice, s.stream));
-        if (m->m64.has_feature)
+        if (m->m64.has_feature && !a->ephemeris)
             CU_CHECK(cudaMemcpy2DAsync(d_earth, pitch, a->earth + (earth_ps ? done : 0),
                                        (size_t)a->earth_stride * sizeof(double),
                                        (size_t)(earth_ps ? cn : 1) * sizeof(double), 3,
@@ -420,6 +454,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         la.out = s.d_out; la.out_stride = m->ws_chunk;
         la.n_peers = 0; la.peer_offset = 0; la.peer_stride = 0;
         set_healpix(la, hp, done);
+        if (a->ephemeris) set_ephemeris(la, a->ephemeris, d_obs);
         if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
         CU_CHECK(launch_eval(m, la, a->precision, s.stream));
         CU_CHECK(cudaEventRecord(s.k1, s.stream));
@@ -565,12 +600,152 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
     la.n_peers = a->n_peers; la.peer_offset = a->peer_offset; la.peer_stride = a->peer_stride;
     for (int p = 0; p < ZODI_MAX_PEERS; ++p) la.peer_out[p] = p < a->n_peers ? a->peer_out[p] : nullptr;
     set_healpix(la, hp, 0);
+    if (a->ephemeris) set_ephemeris(la, a->ephemeris, a->obstime);
     la.cyc_block = a->cyclic_block; la.cyc_parts = a->cyclic_parts; la.cyc_rank = a->cyclic_rank;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
     return ZODI_OK;
 }
 
 int zodi_evaluate(zodi_model_t m, const zodi_eval_args* a) { return evaluate_impl(m, a, nullptr); }
+
+// ---- on-device ephemeris ---------------------------------------------------------------------
+static void spline_to_device_layout(int64_t n_knots, double t0, double dt, const double* knots,
+                                    std::vector<double>& out) {
+    std::vector<double> x(n_knots), c0, c1, c2, c3;
+    for (int64_t k = 0; k < n_knots; ++k) x[k] = t0 + (double)k * dt;  // np.arange(t0, t1 + dt, dt)
+    const int64_t nseg = n_knots - 1;
+    out.assign((size_t)nseg * 12, 0.0);
+    for (int axis = 0; axis < 3; ++axis) {
+        cubic_spline_not_a_knot(x, knots + (size_t)axis * n_knots, c0, c1, c2, c3);
+        for (int64_t i = 0; i < nseg; ++i) {
+            double* o = &out[(size_t)i * 12 + axis * 4];
+            o[0] = c0[i]; o[1] = c1[i]; o[2] = c2[i]; o[3] = c3[i];
+        }
+    }
+}
+
+int zodi_ephemeris_create(int device, const zodi_ephemeris_desc* d, zodi_ephemeris_t* out) {
+    if (!out) return fail(ZODI_ERR_INVALID, "out handle pointer is NULL");
+    *out = nullptr;
+    if (!d || !d->earth_knots) return fail(ZODI_ERR_INVALID, "ephemeris descriptor / earth_knots is NULL");
+    if (d->n_knots < 4) return fail(ZODI_ERR_INVALID, "n_knots=%lld < 4", (long long)d->n_knots);
+    if (!(d->dt > 0.0)) return fail(ZODI_ERR_INVALID, "knot spacing dt must be positive");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    zodi_ephemeris_s* e = new (std::nothrow) zodi_ephemeris_s();
+    if (!e) return fail(ZODI_ERR_NOMEM, "out of host memory");
+    e->device = device; e->n_knots = d->n_knots; e->t0 = d->t0; e->dt = d->dt; e->obs_scale = d->obs_scale;
+    spline_to_device_layout(d->n_knots, d->t0, d->dt, d->earth_knots, e->earth_c);
+    const size_t bytes = e->earth_c.size() * sizeof(double);
+    cudaError_t err = cudaMalloc((void**)&e->d_earth, bytes);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_earth, e->earth_c.data(), bytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess && d->obs_knots) {
+        std::vector<double> oc;
+        spline_to_device_layout(d->n_knots, d->t0, d->dt, d->obs_knots, oc);
+        err = cudaMalloc((void**)&e->d_obs, bytes);
+        if (err == cudaSuccess) err = cudaMemcpy(e->d_obs, oc.data(), bytes, cudaMemcpyHostToDevice);
+    }
+    if (err == cudaSuccess) err = cudaMalloc((void**)&e->d_stats, 3 * sizeof(double));
+    if (err != cudaSuccess) {
+        zodi_ephemeris_destroy(e);
+        return fail(ZODI_ERR_CUDA, "ephemeris upload failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_set_obs_scale(zodi_ephemeris_t e, double obs_scale) {
+    if (!e) return fail(ZODI_ERR_INVALID, "ephemeris handle is NULL");
+    e->obs_scale = obs_scale;
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_destroy(zodi_ephemeris_t e) {
+    if (!e) return ZODI_OK;
+    {
+        DeviceGuard guard(e->device);
+        cudaFree(e->d_earth); cudaFree(e->d_obs); cudaFree(e->d_stats);
+    }
+    delete e;
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_coefficients(zodi_ephemeris_t e, double* c) {
+    if (!e || !c) return fail(ZODI_ERR_INVALID, "NULL argument");
+    const int64_t nseg = e->n_knots - 1;
+    for (int k = 0; k < 4; ++k)
+        for (int64_t i = 0; i < nseg; ++i)
+            for (int axis = 0; axis < 3; ++axis) c[(k * nseg + i) * 3 + axis] = e->earth_c[(size_t)i * 12 + axis * 4 + k];
+    return ZODI_OK;
+}
+
+// stage `t` on the device when it lives on the host; returns the device pointer to use
+static int stage_times(const double* t, int64_t n, int32_t memory, cudaStream_t st, double** d_t, bool* owned) {
+    *owned = false;
+    *d_t = const_cast<double*>(t);
+    if (memory == ZODI_MEM_DEVICE) return ZODI_OK;
+    CU_CHECK(cudaMalloc((void**)d_t, (size_t)n * sizeof(double)));
+    *owned = true;
+    CU_CHECK(cudaMemcpyAsync(*d_t, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_positions(zodi_ephemeris_t e, const double* t, int64_t n, int32_t memory, double* earth_out,
+                             double* obs_out, void* stream) {
+    if (!e || !t || n < 0) return fail(ZODI_ERR_INVALID, "bad argument");
+    if (n == 0) return ZODI_OK;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", e->device);
+    cudaStream_t st = memory == ZODI_MEM_DEVICE ? (cudaStream_t)stream : nullptr;
+    double* d_t; bool owned;
+    int rc = stage_times(t, n, memory, st, &d_t, &owned);
+    if (rc) return rc;
+    double *d_e = earth_out, *d_o = obs_out;
+    if (memory == ZODI_MEM_HOST) {
+        if (earth_out) CU_CHECK(cudaMalloc((void**)&d_e, (size_t)3 * n * sizeof(double)));
+        if (obs_out) CU_CHECK(cudaMalloc((void**)&d_o, (size_t)3 * n * sizeof(double)));
+    }
+    LaunchArgs la;
+    std::memset(&la, 0, sizeof(la));
+    la.n = n;
+    set_ephemeris(la, e, d_t);
+    zodi_ephemeris_positions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(la, d_e, d_o);
+    g_launches.fetch_add(1);
+    CU_CHECK(cudaGetLastError());
+    if (memory == ZODI_MEM_HOST) {
+        if (earth_out) CU_CHECK(cudaMemcpy(earth_out, d_e, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (obs_out) CU_CHECK(cudaMemcpy(obs_out, d_o, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (earth_out) cudaFree(d_e);
+        if (obs_out) cudaFree(d_o);
+    }
+    if (owned) { cudaStreamSynchronize(st); cudaFree(d_t); }
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_stats(zodi_ephemeris_t e, const double* t, int64_t n, int32_t memory, void* stream,
+                         double* stats) {
+    if (!e || !t || !stats || n < 1) return fail(ZODI_ERR_INVALID, "bad argument");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", e->device);
+    cudaStream_t st = memory == ZODI_MEM_DEVICE ? (cudaStream_t)stream : nullptr;
+    double* d_t; bool owned;
+    int rc = stage_times(t, n, memory, st, &d_t, &owned);
+    if (rc) return rc;
+    CU_CHECK(cudaMemsetAsync(e->d_stats, 0, 3 * sizeof(double), st));
+    LaunchArgs la;
+    std::memset(&la, 0, sizeof(la));
+    la.n = n;
+    set_ephemeris(la, e, d_t);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    zodi_ephemeris_stats_kernel<<<grid, 256, 0, st>>>(la, e->d_stats, reinterpret_cast<unsigned long long*>(e->d_stats + 1));
+    g_launches.fetch_add(1);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(stats, e->d_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (owned) cudaFree(d_t);
+    if (!e->d_obs) stats[2] = e->obs_scale * e->obs_scale * stats[1];  // observer = scale * Earth
+    return ZODI_OK;
+}
 
 static int check_healpix(int64_t nside, int64_t ipix_start, int64_t n, int nest) {
     if (nest && (nside & (nside - 1)) != 0)

@@ -38,7 +38,46 @@ struct LaunchArgs {
     int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel vector
     // block-cyclic shard layout (see zodi_eval_args.cyclic_block); 0 = identity
     int64_t cyc_block;    int cyc_parts;      int cyc_rank;
+    // on-device ephemeris (time-ordered data): positions from cubic splines at obstime[j]
+    const double* eph_coef;   // [n_knots-1][3][4] Earth (highest power first); NULL = use obs/earth arrays
+    const double* eph_obs_coef;  // same for the observer, or NULL: observer = eph_scale * Earth
+    const double* obstime;
+    int64_t eph_nseg;     double eph_t0, eph_dt, eph_scale;
 };
+
+// Spline position at time t: interval i = floor((t - t0)/dt) clamped to the spline (scipy's PPoly
+// extrapolates with the end polynomials), value = ((c0 s + c1) s + c2) s + c3 with s = t - knot_i.
+__device__ __forceinline__ void spline_position(const double* __restrict__ coef, int64_t nseg, double t0,
+                                                double dt, double t, double& x, double& y, double& z) {
+    int64_t i = (int64_t)floor((t - t0) / dt);
+    i = i < 0 ? 0 : (i > nseg - 1 ? nseg - 1 : i);
+    const double s = t - (t0 + (double)i * dt);
+    const double* c = coef + i * 12;
+    x = fma(fma(fma(c[0], s, c[1]), s, c[2]), s, c[3]);
+    y = fma(fma(fma(c[4], s, c[5]), s, c[6]), s, c[7]);
+    z = fma(fma(fma(c[8], s, c[9]), s, c[10]), s, c[11]);
+}
+
+// Observer and Earth position of line of sight jj: arrays of the reference seam, or the splines.
+__device__ __forceinline__ void load_positions(const LaunchArgs& a, int64_t jj, bool need_earth, double& ox,
+                                               double& oy, double& oz, double& ex, double& ey) {
+    if (a.eph_coef != nullptr) {
+        const double t = a.obstime[jj];
+        double ez;
+        spline_position(a.eph_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, ex, ey, ez);
+        if (a.eph_obs_coef != nullptr) spline_position(a.eph_obs_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, ox, oy, oz);
+        else { ox = a.eph_scale * ex; oy = a.eph_scale * ey; oz = a.eph_scale * ez; }
+        return;
+    }
+    const int64_t jo = a.obs_per_sample ? jj : 0;
+    ox = a.obs[jo]; oy = a.obs[a.obs_stride + jo]; oz = a.obs[2 * a.obs_stride + jo];
+    ex = 0.0; ey = 0.0;
+    if (need_earth) {
+        const int64_t je = a.earth_per_sample ? jj : 0;
+        ex = a.earth[je];
+        ey = a.earth[a.earth_stride + je];
+    }
+}
 
 // Global index of local line of sight j under the (optional) block-cyclic layout.
 __device__ __forceinline__ int64_t global_index(const LaunchArgs& a, int64_t j) {
@@ -115,15 +154,8 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
 
     double ux, uy, uz;
     load_direction(args, jj, ux, uy, uz);
-    const int64_t jo = args.obs_per_sample ? jj : 0;
-    const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
-                 oz = args.obs[2 * args.obs_stride + jo];
-    double ex = 0.0, ey = 0.0;
-    if (model.has_feature) {
-        const int64_t je = args.earth_per_sample ? jj : 0;
-        ex = args.earth[je];
-        ey = args.earth[args.earth_stride + je];
-    }
+    double ox, oy, oz, ex, ey;
+    load_positions(args, jj, model.has_feature != 0, ox, oy, oz, ex, ey);
 
     Real total = Real(0);
     integrate_line_of_sight<Real>(
@@ -166,15 +198,8 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
 
     double ux, uy, uz;
     load_direction(args, jj, ux, uy, uz);
-    const int64_t jo = args.obs_per_sample ? jj : 0;
-    const double ox = args.obs[jo], oy = args.obs[args.obs_stride + jo],
-                 oz = args.obs[2 * args.obs_stride + jo];
-    double ex = 0.0, ey = 0.0;
-    if (HAS_RF) {
-        const int64_t je = args.earth_per_sample ? jj : 0;
-        ex = args.earth[je];
-        ey = args.earth[args.earth_stride + je];
-    }
+    double ox, oy, oz, ex, ey;
+    load_positions(args, jj, HAS_RF, ox, oy, oz, ex, ey);
 
     Real total = Real(0);
     integrate_kelsall<Real, HAS_RF, SCATTER, SHARE13>(
@@ -214,14 +239,9 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
         const int64_t jj = q ? jj1 : jj0;
         double ux, uy, uz;
         load_direction(args, jj, ux, uy, uz);
-        const int64_t jo = args.obs_per_sample ? jj : 0;
-        G[q] = los_geometry<float>(ux, uy, uz, args.obs[jo], args.obs[args.obs_stride + jo],
-                                   args.obs[2 * args.obs_stride + jo]);
-        if (HAS_RF) {
-            const int64_t je = args.earth_per_sample ? jj : 0;
-            ex[q] = args.earth[je];
-            ey[q] = args.earth[args.earth_stride + je];
-        }
+        double ox, oy, oz;
+        load_positions(args, jj, HAS_RF, ox, oy, oz, ex[q], ey[q]);
+        G[q] = los_geometry<float>(ux, uy, uz, ox, oy, oz);
     }
 
     float tot0 = 0.f, tot1 = 0.f;
@@ -257,6 +277,50 @@ __global__ void zodi_healpix_vectors_kernel(const __grid_constant__ LaunchArgs a
     double ux, uy, uz;
     load_direction(args, j, ux, uy, uz);
     out[j] = ux; out[out_stride + j] = uy; out[2 * out_stride + j] = uz;
+}
+
+// Spline positions at n times (tests / users): earth_out, obs_out (3, n) or NULL.
+__global__ void zodi_ephemeris_positions_kernel(const __grid_constant__ LaunchArgs a, double* __restrict__ earth_out,
+                                                double* __restrict__ obs_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n) return;
+    const double t = a.obstime[j];
+    double ex, ey, ez, ox, oy, oz;
+    spline_position(a.eph_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, ex, ey, ez);
+    if (a.eph_obs_coef != nullptr) spline_position(a.eph_obs_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, ox, oy, oz);
+    else { ox = a.eph_scale * ex; oy = a.eph_scale * ey; oz = a.eph_scale * ez; }
+    if (earth_out) { earth_out[j] = ex; earth_out[a.n + j] = ey; earth_out[2 * a.n + j] = ez; }
+    if (obs_out) { obs_out[j] = ox; obs_out[a.n + j] = oy; obs_out[2 * a.n + j] = oz; }
+}
+
+// Reductions over the samples: stats[0] += sum |earth|^2, stats[1] = max |earth|^2 (as bits),
+// stats[2] = max |observer|^2 (as bits; only when the observer has its own spline).
+__global__ void zodi_ephemeris_stats_kernel(const __grid_constant__ LaunchArgs a, double* __restrict__ sum_out,
+                                            unsigned long long* __restrict__ max_bits) {
+    double sum = 0.0, me = 0.0, mo = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+        const double t = a.obstime[j];
+        double x, y, z;
+        spline_position(a.eph_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, x, y, z);
+        const double r2 = x * x + y * y + z * z;
+        sum += r2;
+        me = fmax(me, r2);
+        if (a.eph_obs_coef != nullptr) {
+            spline_position(a.eph_obs_coef, a.eph_nseg, a.eph_t0, a.eph_dt, t, x, y, z);
+            mo = fmax(mo, x * x + y * y + z * z);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        me = fmax(me, __shfl_xor_sync(0xffffffffu, me, off));
+        mo = fmax(mo, __shfl_xor_sync(0xffffffffu, mo, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sum_out, sum);
+        atomicMax(max_bits, (unsigned long long)__double_as_longlong(me));
+        atomicMax(max_bits + 1, (unsigned long long)__double_as_longlong(mo));
+    }
 }
 
 // max over observers of r^2 = x^2+y^2+z^2 (for the global early-out flags, quirk Q1).

@@ -246,4 +246,53 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     b.cutF_in = a.cutF_in; b.cutF_out = a.cutF_out;
 }
 
+// Not-a-knot cubic spline through uniformly or non-uniformly spaced knots, one axis: the same
+// linear system scipy.interpolate.CubicSpline (bc_type="not-a-knot", n >= 4) solves for the knot
+// derivatives, then its PPoly coefficients c[k][i] (highest power first) on interval i.
+inline void cubic_spline_not_a_knot(const std::vector<double>& x, const double* y, std::vector<double>& c0,
+                                    std::vector<double>& c1, std::vector<double>& c2, std::vector<double>& c3) {
+    const int n = (int)x.size();
+    std::vector<double> dx(n - 1), slope(n - 1);
+    for (int i = 0; i < n - 1; ++i) { dx[i] = x[i + 1] - x[i]; slope[i] = (y[i + 1] - y[i]) / dx[i]; }
+    // tridiagonal system lo[i] s[i-1] + di[i] s[i] + up[i] s[i+1] = b[i]
+    std::vector<double> lo(n, 0.0), di(n, 0.0), up(n, 0.0), b(n, 0.0), s(n, 0.0);
+    for (int i = 1; i < n - 1; ++i) {
+        lo[i] = dx[i];
+        di[i] = 2.0 * (dx[i - 1] + dx[i]);
+        up[i] = dx[i - 1];
+        b[i] = 3.0 * (dx[i] * slope[i - 1] + dx[i - 1] * slope[i]);
+    }
+    {   // not-a-knot at the first interior knot
+        const double d = x[2] - x[0];
+        di[0] = dx[1];
+        up[0] = d;
+        b[0] = ((dx[0] + 2.0 * d) * dx[1] * slope[0] + dx[0] * dx[0] * slope[1]) / d;
+    }
+    {   // not-a-knot at the last interior knot
+        const double d = x[n - 1] - x[n - 3];
+        di[n - 1] = dx[n - 3];
+        lo[n - 1] = d;
+        b[n - 1] = (dx[n - 2] * dx[n - 2] * slope[n - 3] + (2.0 * d + dx[n - 2]) * dx[n - 3] * slope[n - 2]) / d;
+    }
+    // Thomas algorithm with partial safety (the matrix is diagonally dominant in the interior)
+    std::vector<double> cp(n, 0.0), dp(n, 0.0);
+    cp[0] = up[0] / di[0];
+    dp[0] = b[0] / di[0];
+    for (int i = 1; i < n; ++i) {
+        const double m = di[i] - lo[i] * cp[i - 1];
+        cp[i] = up[i] / m;
+        dp[i] = (b[i] - lo[i] * dp[i - 1]) / m;
+    }
+    s[n - 1] = dp[n - 1];
+    for (int i = n - 2; i >= 0; --i) s[i] = dp[i] - cp[i] * s[i + 1];
+    c0.resize(n - 1); c1.resize(n - 1); c2.resize(n - 1); c3.resize(n - 1);
+    for (int i = 0; i < n - 1; ++i) {
+        const double t = (s[i] + s[i + 1] - 2.0 * slope[i]) / dx[i];
+        c0[i] = t / dx[i];
+        c1[i] = (slope[i] - s[i]) / dx[i] - t;
+        c2[i] = s[i];
+        c3[i] = y[i];
+    }
+}
+
 }  // namespace zodi

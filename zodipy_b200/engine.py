@@ -45,6 +45,106 @@ def _rows(a, name: str):
     return a, a.ctypes.data, a.shape[1], stride
 
 
+MEAN_DIST_TO_L2 = 0.009896235034000056  # AU, zodipy/bodies.py:13
+
+
+class DeviceEphemeris:
+    """Earth / observer ephemeris as device-resident cubic splines (time-ordered data).
+
+    ``earth_knots`` (3, K): Earth's heliocentric ecliptic position [AU] at the uniformly spaced times
+    ``t0 + k * dt`` - what the reference samples hourly with Astropy and interpolates with SciPy's
+    ``CubicSpline`` (``zodipy/bodies.py:16-35``).  ``obs_knots``: the observer's knots, or ``None``
+    for an observer tied to Earth: ``obspos="earth"`` (scale 1) or ``"semb-l2"`` (scale set per
+    evaluation from the samples, reproducing ``bodies.py:38-50`` including its un-axised norm).
+    """
+
+    def __init__(self, t0: float, dt: float, earth_knots, obs_knots=None, device: int = 0):
+        self._lib = _cabi.load()
+        self.device = int(device)
+        earth = np.ascontiguousarray(earth_knots, dtype=np.float64)
+        if earth.ndim != 2 or earth.shape[0] != 3:
+            raise ValueError("earth_knots must have shape (3, n_knots)")
+        d = _cabi.EphemerisDesc()
+        d.n_knots, d.t0, d.dt, d.obs_scale = earth.shape[1], float(t0), float(dt), 1.0
+        d.earth_knots = _cabi.as_double_p(earth)
+        obs = None
+        if obs_knots is not None:
+            obs = np.ascontiguousarray(obs_knots, dtype=np.float64)
+            if obs.shape != earth.shape:
+                raise ValueError("obs_knots must have the shape of earth_knots")
+            d.obs_knots = _cabi.as_double_p(obs)
+        self.n_knots, self.t0, self.dt = earth.shape[1], float(t0), float(dt)
+        self.has_obs_knots = obs is not None
+        self._handle = C.c_void_p()
+        _cabi.check(self._lib.zodi_ephemeris_create(self.device, C.byref(d), C.byref(self._handle)))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.zodi_ephemeris_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_obs_scale(self, scale: float) -> None:
+        _cabi.check(self._lib.zodi_ephemeris_set_obs_scale(self._handle, float(scale)))
+
+    def coefficients(self) -> np.ndarray:
+        """Earth spline coefficients in scipy's ``CubicSpline.c`` layout (4, n_knots - 1, 3)."""
+        c = np.empty((4, self.n_knots - 1, 3), dtype=np.float64)
+        _cabi.check(self._lib.zodi_ephemeris_coefficients(self._handle, _cabi.as_double_p(c)))
+        return c
+
+    def _times(self, t):
+        if _is_torch(t):
+            import torch
+
+            if t.dtype != torch.float64 or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError("device obstime must be a contiguous float64 CUDA tensor")
+            return t, t.data_ptr(), t.numel(), _cabi.MEM_DEVICE, torch.cuda.current_stream(t.device).cuda_stream
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
+        return t, t.ctypes.data, t.size, _cabi.MEM_HOST, None
+
+    def positions(self, t):
+        """(earth, obs) positions (3, n) at times ``t`` from the device splines (NumPy in/out)."""
+        t_a, ptr, n, mem, stream = self._times(np.asarray(t, dtype=np.float64))
+        earth, obs = np.empty((3, n)), np.empty((3, n))
+        _cabi.check(self._lib.zodi_ephemeris_positions(self._handle, ptr, n, mem, earth.ctypes.data,
+                                                       obs.ctypes.data, stream))
+        return earth, obs
+
+    def stats(self, t):
+        """(sum |earth|^2, max |earth|, max |observer|) over the samples at times ``t``."""
+        t_a, ptr, n, mem, stream = self._times(t)
+        out = (C.c_double * 3)()
+        _cabi.check(self._lib.zodi_ephemeris_stats(self._handle, ptr, n, mem, stream, out))
+        return out[0], float(np.sqrt(out[1])), float(np.sqrt(out[2]))
+
+    def prepare(self, t, observer: str = "earth"):
+        """Set the observer rule for the samples at times ``t`` and return the largest observer
+        distance (for the global early-out flags).  observer: "earth" | "semb-l2" | "knots"."""
+        if observer == "knots":
+            if not self.has_obs_knots:
+                raise ValueError("this ephemeris has no observer knots")
+            return self.stats(t)[2]
+        if self.has_obs_knots:
+            raise ValueError("this ephemeris carries observer knots; use observer='knots'")
+        if observer not in ("earth", "semb-l2"):
+            raise ValueError("observer must be 'earth', 'semb-l2' or 'knots'")
+        self.set_obs_scale(1.0)
+        sum_r2, max_earth, _ = self.stats(t)
+        scale = 1.0
+        if observer == "semb-l2":
+            # get_semb_l2_pos: earth / ||earth|| * (||earth|| + L2) with the norm over the WHOLE array
+            norm = float(np.sqrt(sum_r2))
+            scale = (norm + MEAN_DIST_TO_L2) / norm
+            self.set_obs_scale(scale)
+        return scale * max_earth
+
+
 class DeviceModel:
     """Device-resident model parameters + the evaluate call."""
 
@@ -94,13 +194,18 @@ class DeviceModel:
     def outside_flags(self, obs) -> np.ndarray:
         return spec_outside_flags(self.spec, self.max_observer_radius(obs))
 
-    def evaluate(self, u, obs, earth=None, *, return_comps: bool = False, precision: str = "fp64",
-                 out=None, out_dtype=None, outside_flags=None, peer_map=None):
+    def evaluate(self, u, obs=None, earth=None, *, return_comps: bool = False, precision: str = "fp64",
+                 out=None, out_dtype=None, outside_flags=None, peer_map=None, ephemeris=None,
+                 obstime=None, observer: str = "earth"):
         """Emission [MJy/sr] for unit vectors ``u`` (3, N).
 
         ``obs`` / ``earth``: (3,), (3, 1) or (3, N) [AU]; ``earth`` defaults to ``obs``.
         ``outside_flags``: optional (ncomps, 2) uint8 GLOBAL early-out flags (needed when the
         observers of a job are sharded over several calls/GPUs); default: derived from ``obs``.
+        ``ephemeris`` + ``obstime``: time-ordered data with positions evaluated on the device from a
+        :class:`DeviceEphemeris` at the per-sample times ``obstime`` (n,) (``obs`` / ``earth`` are
+        then not needed); ``observer`` selects "earth", "semb-l2" or the ephemeris' own observer
+        "knots".
         ``peer_map``: a :class:`zodipy_b200.sharding.PeerMap`; the kernel then stores this call's
         slice directly into every GPU's full map (fused all-gather) and nothing is returned.
         Returns an array like the inputs (NumPy -> NumPy, torch CUDA -> torch CUDA) of shape
@@ -108,10 +213,15 @@ class DeviceModel:
         """
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
-        if earth is None:
-            earth = obs
         device_mem = _is_torch(u)
         u_a, u_ptr, n, u_stride = _rows(u, "unit_vectors")
+        if ephemeris is not None:
+            return self._evaluate_tod(u_a, u_ptr, n, u_stride, device_mem, ephemeris, obstime, observer,
+                                      return_comps, precision, out, out_dtype, outside_flags)
+        if obs is None:
+            raise ValueError("obs is required unless an ephemeris is given")
+        if earth is None:
+            earth = obs
         if device_mem:
             import torch
 
@@ -191,6 +301,53 @@ class DeviceModel:
             args.peer_offset, args.peer_stride = peer_map.offset, peer_map.n_total
             if peer_map.cyclic is not None:
                 args.cyclic_block, args.cyclic_parts, args.cyclic_rank = peer_map.cyclic
+        _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
+        return out
+
+    def _evaluate_tod(self, u_a, u_ptr, n, u_stride, device_mem, ephemeris, obstime, observer,
+                      return_comps, precision, out, out_dtype, outside_flags):
+        if obstime is None:
+            raise ValueError("obstime is required with an ephemeris")
+        if ephemeris.device != self.device:
+            raise ValueError("ephemeris and model live on different devices")
+        if device_mem != _is_torch(obstime):
+            raise ValueError("u and obstime must both be NumPy arrays or both torch CUDA tensors")
+        t_a, t_ptr, nt, _, stream = ephemeris._times(obstime)
+        if nt != n:
+            raise ValueError("obstime must hold one time per unit vector")
+        out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        shape = (self.ncomps, n) if return_comps else (n,)
+        if device_mem:
+            import torch
+
+            tdtype = torch.float64 if out_dtype == np.float64 else torch.float32
+            if out is None:
+                out = torch.empty(shape, dtype=tdtype, device=u_a.device)
+            elif tuple(out.shape) != shape or out.dtype != tdtype or not out.is_contiguous():
+                raise ValueError("out has wrong shape/dtype or is not contiguous")
+            out_ptr = out.data_ptr()
+        else:
+            if out is None:
+                out = np.empty(shape, dtype=out_dtype)
+            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            out_ptr = out.ctypes.data
+        if n == 0:
+            return out
+        r_max = ephemeris.prepare(t_a, observer)
+        flags = spec_outside_flags(self.spec, r_max) if outside_flags is None else \
+            np.ascontiguousarray(outside_flags, dtype=np.uint8)
+        args = _cabi.EvalArgs()
+        args.n = n
+        args.u, args.u_stride = u_ptr, u_stride
+        args.outside_flags = flags.ctypes.data_as(_cabi.c_uint8_p)
+        args.return_comps = int(bool(return_comps))
+        args.precision = _PRECISIONS[precision]
+        args.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
+        args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
+        args.out, args.out_stride = out_ptr, n
+        args.stream = stream
+        args.ephemeris, args.obstime = ephemeris._handle, t_ptr
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 

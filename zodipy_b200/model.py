@@ -106,6 +106,22 @@ class Model:
             precision=precision or self._precision, out=out, out_dtype=out_dtype,
             outside_flags=outside_flags)
 
+    def evaluate_tod_xyz(self, unit_vectors, obstime, ephemeris, *, observer: str = "earth",
+                         return_comps: bool = False, precision: str | None = None, out=None,
+                         out_dtype=None):
+        """Time-ordered data with Earth / observer positions interpolated ON THE DEVICE
+        (additive entry).
+
+        ``ephemeris``: a :class:`zodipy_b200.engine.DeviceEphemeris` built from positions at
+        uniformly spaced knots (the reference's hourly grid, ``zodipy/bodies.py:16-35``);
+        ``obstime`` (N,): per-sample times in the knots' unit; ``observer``: "earth", "semb-l2" or
+        "knots".  Equivalent to ``evaluate_xyz(u, obs_xyz(t), earth_xyz(t))`` with the positions
+        from ``scipy.interpolate.CubicSpline`` - without computing or uploading them on the host.
+        """
+        return self.device_model.evaluate(
+            unit_vectors, return_comps=return_comps, precision=precision or self._precision, out=out,
+            out_dtype=out_dtype, ephemeris=ephemeris, obstime=obstime, observer=observer)
+
     def evaluate_healpix(self, nside: int, obs_xyz, earth_xyz=None, *, frame_rotation=None,
                          pix_range=None, nest: bool = False, return_comps: bool = False,
                          precision: str | None = None, out=None, out_dtype=None, device_out: bool = False):
