@@ -96,6 +96,48 @@ def run(label, model, u, obs, earth, skip_fp64_above):
     return res
 
 
+def tod_e2e(dev, n=20_000_000):
+    """Time-ordered data END TO END from pinned host memory: (a) the reference's array seam with
+    per-sample observer/Earth arrays (72 B per sample up), (b) on-device ephemeris splines
+    (pointing + time, 32 B per sample up)."""
+    import time
+
+    from scipy.interpolate import CubicSpline
+
+    t0, dt = 59215.0, 1.0 / 24.0
+    n_knots = 366 * 24
+    tk = t0 + dt * np.arange(n_knots)
+    lon = 2 * np.pi * (tk - t0) / 365.25 + 1.7
+    r = 1.0 - 0.0167 * np.cos(lon - 1.8)
+    earth_knots = np.array([r * np.cos(lon), r * np.sin(lon), 1e-5 * np.sin(3 * lon)])
+    t = np.linspace(t0, t0 + 365.0, n)
+    u_dev, _, _ = tod_inputs(n, dev)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    u = pin(u_dev.cpu().numpy())
+    del u_dev
+    tic = time.perf_counter()
+    earth = CubicSpline(tk, earth_knots, axis=-1)(t)  # what the reference does per sample on the host
+    host_interp_s = time.perf_counter() - tic
+    earth, t_p = pin(earth), pin(t)
+    out = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+    model = zp.Model(zp.Quantity(25.0, "um"), precision="fp32")
+    eph = engine.DeviceEphemeris(t0, dt, earth_knots)
+    res = {"config": f"4e: TOD e2e {n:.0e} samples from pinned host memory, dirbe 25um, observer=earth",
+           "host_cubicspline_seconds_not_timed_below": host_interp_s}
+    for label, call in (
+            ("array_seam_72B_per_sample", lambda: model.evaluate_xyz(u, earth, earth, out=out, out_dtype=np.float32)),
+            ("device_ephemeris_32B_per_sample", lambda: model.evaluate_tod_xyz(u, t_p, eph, out=out, out_dtype=np.float32))):
+        call()
+        torch.cuda.synchronize()
+        tic = time.perf_counter()
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - tic) / 3 * 1e3
+        res[label] = {"ms": ms, "evals_per_s": n * 6 * 50 / (ms * 1e-3), "result_sum": float(out.sum(dtype=np.float64))}
+    print(json.dumps(res), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-n", type=float, default=2.1e8)
@@ -121,6 +163,7 @@ def main():
     if args.max_n >= 12 * 4096 * 4096:
         run("5: planck13 545GHz nside=4096", zp.Model(Q(545.0, "GHz"), name="planck13"), healpix_dirs(4096, dev),
             earth, earth, 3e8)
+    tod_e2e(dev)
     # extra: scattering branch and the generic kernel (RRM)
     run("extra: dirbe 1.25um (scattering) nside=512", zp.Model(Q(1.25, "um")), healpix_dirs(512, dev), earth, earth,
         args.skip_fp64_above)

@@ -86,3 +86,30 @@ def prepare_arrays(skycoord, obspos, obspos_isstr, interp_obstimes, ephemeris):
 
 def as_mjy_per_sr(emission):
     return emission << (units.MJy / units.sr)
+
+
+def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device):
+    """Hourly Earth (and observer-body) knots as a device-resident spline
+    (:class:`zodipy_b200.engine.DeviceEphemeris`) for time-ordered data with a string ``obspos``.
+
+    Same knots as the host path (``arrange_obstimes`` + ``get_body``, ``bodies.py:16-35``); the
+    per-sample interpolation and the SEMB-L2 scaling then happen in the kernel prologue instead of
+    ``CubicSpline(...)(obstimes)`` on the host.  Returns (ephemeris, observer_mode, ecliptic unit
+    vectors, sample times in MJD).
+    """
+    from .engine import DeviceEphemeris
+
+    knots_mjd = interp_obstimes.mjd
+    earth_knots = _body_xyz("earth", interp_obstimes, ephemeris)
+    obs_knots, mode = None, obspos
+    if obspos not in ("earth", "semb-l2"):
+        try:
+            obs_knots = _body_xyz(obspos, interp_obstimes, ephemeris)
+        except KeyError as error:
+            valid = [*coords.solar_system_ephemeris.bodies, "semb-l2"]
+            raise ValueError(f"Invalid observer string: '{obspos}'. Valid observers are: {valid}") from error
+        mode = "knots"
+    eph = DeviceEphemeris(float(knots_mjd[0]), 1.0 / 24.0, earth_knots, obs_knots, device=device)
+    ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
+    u_xyz = np.ascontiguousarray(ecl.cartesian.xyz.value)
+    return eph, mode, u_xyz, np.ascontiguousarray(skycoord.obstime.mjd, dtype=np.float64)

@@ -8,7 +8,9 @@ that seam directly (no Astropy): it is what the benchmarks, the parity tests and
 sharding use.
 
 Additive, defaulted knobs (not in the reference): ``precision`` ("fp64" faithful | "fp32" fast),
-``device`` (CUDA ordinal; default ``LOCAL_RANK`` or 0).  ``nprocesses`` is accepted for API
+``device`` (CUDA ordinal; default ``LOCAL_RANK`` or 0), ``tod_ephemeris`` ("host": per-sample
+positions interpolated with SciPy as in the reference | "device": hourly knots uploaded once and
+interpolated in the kernel prologue).  ``nprocesses`` is accepted for API
 compatibility and ignored: the GPU path has no use for host worker processes.
 """
 from __future__ import annotations
@@ -30,7 +32,8 @@ class Model:
 
     def __init__(self, x, *, weights=None, name: str = "dirbe", gauss_quad_degree: int = 50,
                  extrapolate: bool = False, ephemeris: str = "builtin",
-                 precision: str = "fp64", device: int | None = None) -> None:
+                 precision: str = "fp64", device: int | None = None,
+                 tod_ephemeris: str = "host") -> None:
         try:
             if not x.isscalar and weights is None:
                 raise ValueError("Bandpass weights must be provided for non-scalar `x`.")
@@ -58,6 +61,9 @@ class Model:
 
         if precision not in ("fp64", "fp32"):
             raise ValueError("precision must be 'fp64' or 'fp32'")
+        if tod_ephemeris not in ("host", "device"):
+            raise ValueError("tod_ephemeris must be 'host' or 'device'")
+        self._tod_ephemeris = tod_ephemeris
         self._x = x
         self._bounds_error = not extrapolate
         self._normalized_weights = normalized_weights
@@ -164,6 +170,12 @@ class Model:
         interp_obstimes = None
         if skycoord.obstime.size != 1:
             interp_obstimes = astro.arrange_obstimes(skycoord.obstime[0].mjd, skycoord.obstime[-1].mjd)
+            if obspos_isstr and self._tod_ephemeris == "device" and interp_obstimes.size >= 4:
+                # hourly knots -> device splines; per-sample interpolation in the kernel prologue
+                eph, mode, u_xyz, mjd = astro.device_ephemeris(skycoord, obspos, interp_obstimes,
+                                                               self._ephemeris, self._device)
+                emission = self.evaluate_tod_xyz(u_xyz, mjd, eph, observer=mode, return_comps=return_comps)
+                return astro.as_mjy_per_sr(emission)
         earth_xyz, obs_xyz, u_xyz = astro.prepare_arrays(
             skycoord, obspos, obspos_isstr, interp_obstimes, self._ephemeris)
         emission = self.evaluate_xyz(u_xyz, obs_xyz, earth_xyz, return_comps=return_comps)
