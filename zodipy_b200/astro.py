@@ -109,7 +109,10 @@ def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device):
             valid = [*coords.solar_system_ephemeris.bodies, "semb-l2"]
             raise ValueError(f"Invalid observer string: '{obspos}'. Valid observers are: {valid}") from error
         mode = "knots"
-    eph = DeviceEphemeris(float(knots_mjd[0]), 1.0 / 24.0, earth_knots, obs_knots, device=device)
+    # np.arange(t0, t1 + dt, dt) fills t0 + k * delta with delta = (t0 + dt) - t0 (NOT exactly dt):
+    # use the array's own spacing so the device knots equal the reference's knot times bit for bit
+    delta = float(knots_mjd[1] - knots_mjd[0])
+    eph = DeviceEphemeris(float(knots_mjd[0]), delta, earth_knots, obs_knots, device=device)
     ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
     u_xyz = np.ascontiguousarray(ecl.cartesian.xyz.value)
     return eph, mode, u_xyz, np.ascontiguousarray(skycoord.obstime.mjd, dtype=np.float64)
