@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "zodi_kernels.cuh"
@@ -306,11 +307,25 @@ int max_r_device(zodi_model_s* m, const double* d_obs, int64_t n_obs, int64_t st
 }
 
 double max_r_host(const double* obs, int64_t n_obs, int64_t stride) {
+    auto range_max = [&](int64_t lo, int64_t hi) {
+        double m = 0.0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const double x = obs[i], y = obs[stride + i], z = obs[2 * stride + i];
+            m = std::fmax(m, x * x + y * y + z * z);
+        }
+        return m;
+    };
+    if (n_obs < (1 << 20)) return std::sqrt(range_max(0, n_obs));
+    // time-ordered data: one pass over 24 B per sample, split over the host cores
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max(1u, std::min(16u, hw ? hw : 4u));
+    std::vector<double> part(nt, 0.0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&, t] { part[t] = range_max(n_obs * t / nt, n_obs * (t + 1) / nt); });
+    for (auto& th : pool) th.join();
     double m = 0.0;
-    for (int64_t i = 0; i < n_obs; ++i) {
-        const double x = obs[i], y = obs[stride + i], z = obs[2 * stride + i];
-        m = std::fmax(m, x * x + y * y + z * z);
-    }
+    for (double v : part) m = std::fmax(m, v);
     return std::sqrt(m);
 }
 
