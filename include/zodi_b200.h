@@ -250,6 +250,14 @@ int zodi_peer_buffer_open(int device, const uint8_t handle[ZODI_IPC_HANDLE_BYTES
 int zodi_peer_buffer_close(int device, void* ptr);
 int zodi_peer_buffer_free(int device, void* ptr);
 
+/* ---- component densities on a set of points -------------------------------------------------
+ * Replaces the array part of grid_number_density (zodipy/number_density.py:482-536): the number
+ * density of every component at n heliocentric ecliptic points xyz (3, n) [AU], for one Earth
+ * position earth[3] (host memory; used by the Earth-trailing feature).  out: (n_comps, n) float64.
+ * xyz / out live in `memory`. */
+int zodi_number_density(zodi_model_t model, const double* xyz, int64_t n, int64_t xyz_stride,
+                        const double* earth, double* out, int64_t out_stride, int32_t memory, void* stream);
+
 /* ---- measurement support ------------------------------------------------------------------ */
 typedef enum {
     ZODI_PEAK_FP32_FMA = 0, /* FFMA  : flop/s (2 per FMA)      */

@@ -355,3 +355,25 @@ def test_evaluate_tod_on_device_equals_host_interpolation(observer, precision):
     sel = np.arange(0, n, 40)
     ref_o = oracle.evaluate(model.spec, u[:, sel], obs[:, sel], earth[:, sel])
     assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
+
+
+@pytest.mark.parametrize("name", ["dirbe", "planck18", "rrm-experimental"])
+def test_grid_number_density_matches_reference_functions(name):
+    """grid_number_density (reference tests/test_model.py:94-123: shape; here also values against
+    the oracle's restatement of the 11 density functions)."""
+    x = np.linspace(-5, 5, 40)
+    y = np.linspace(-5, 5, 30)
+    z = np.linspace(-2, 2, 20)
+    earth = EARTH_20220114[:, 0]
+    grid = zp.grid_number_density_xyz(x, y, z, earth, model=name)
+    model = zp.Model(zp.Quantity(25.0, "um") if name != "planck18" else zp.Quantity(857.0, "GHz"), name=name)
+    assert grid.shape == (model.ncomps, 30, 40, 20)
+    pts = np.asarray(np.meshgrid(x, y, z)).reshape(3, -1)
+    for ci, comp in enumerate(model.spec["comps"]):
+        with np.errstate(all="ignore"):
+            ref = np.broadcast_to(oracle.DENSITY[comp["type"]](pts, comp["params"], EARTH_20220114), pts.shape[1:])
+        got = grid[ci].reshape(-1)
+        scale = np.nanmax(np.abs(ref))
+        np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-13 * scale, err_msg=comp["label"])
+    with pytest.raises(TypeError):
+        zp.grid_number_density_xyz(x, y, z, earth, model=3)

@@ -114,6 +114,8 @@ SYMBOLS = {
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),
     "zodi_flags_from_radius": (C.c_int, [C.c_void_p, C.c_double, c_uint8_p]),
+    "zodi_number_density": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
+                                      C.c_int64, C.c_int32, C.c_void_p]),
     "zodi_peer_buffer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), c_uint8_p]),
     "zodi_peer_buffer_open": (C.c_int, [C.c_int, c_uint8_p, C.POINTER(C.c_void_p)]),
     "zodi_peer_buffer_close": (C.c_int, [C.c_int, C.c_void_p]),

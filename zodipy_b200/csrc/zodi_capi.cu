@@ -822,6 +822,41 @@ int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_s
     return ZODI_OK;
 }
 
+int zodi_number_density(zodi_model_t m, const double* xyz, int64_t n, int64_t xyz_stride, const double* earth,
+                        double* out, int64_t out_stride, int32_t memory, void* stream) {
+    if (!m || !xyz || !earth || !out || n < 0 || xyz_stride < n || out_stride < n)
+        return fail(ZODI_ERR_INVALID, "bad argument");
+    if (n == 0) return ZODI_OK;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", m->device);
+    const int nc = m->desc.n_comps;
+    const double* d_xyz = xyz;
+    double* d_out = out;
+    int64_t ld_in = xyz_stride, ld_out = out_stride;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (memory == ZODI_MEM_HOST) {
+        st = nullptr;
+        double* tmp = nullptr;
+        CU_CHECK(cudaMalloc((void**)&tmp, (size_t)(3 + nc) * n * sizeof(double)));
+        d_xyz = tmp; d_out = tmp + 3 * n; ld_in = n; ld_out = n;
+        cudaError_t e = cudaMemcpy2D(tmp, (size_t)n * sizeof(double), xyz, (size_t)xyz_stride * sizeof(double),
+                                     (size_t)n * sizeof(double), 3, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(tmp); return fail(ZODI_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
+    }
+    // the density kernel reads the raw-to-device-form constants but needs amplitude-free semantics:
+    // density<Real>() returns the full reference density (amplitudes included) for the generic model
+    zodi_number_density_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->m64, d_xyz, n, ld_in, earth[0],
+                                                                          earth[1], d_out, ld_out);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && memory == ZODI_MEM_HOST)
+        e = cudaMemcpy2D(out, (size_t)out_stride * sizeof(double), d_out, (size_t)n * sizeof(double),
+                         (size_t)n * sizeof(double), nc, cudaMemcpyDeviceToHost);
+    if (memory == ZODI_MEM_HOST) cudaFree(const_cast<double*>(d_xyz));
+    if (e != cudaSuccess) return fail(ZODI_ERR_CUDA, "number density failed: %s", cudaGetErrorString(e));
+    return ZODI_OK;
+}
+
 const char* zodi_model_kernel_name(zodi_model_t m) {
     if (!m) return "";
     return (m->kelsall_ok && !m->force_generic) ? "zodi_los_kelsall_kernel" : "zodi_los_generic_kernel";

@@ -279,6 +279,21 @@ __global__ void zodi_healpix_vectors_kernel(const __grid_constant__ LaunchArgs a
     out[j] = ux; out[out_stride + j] = uy; out[2 * out_stride + j] = uz;
 }
 
+// Number density of every component at n points (grid_number_density, number_density.py:482-536).
+__global__ void zodi_number_density_kernel(const __grid_constant__ DevModel<double> model,
+                                           const double* __restrict__ xyz, int64_t n, int64_t stride,
+                                           double ex, double ey, double* __restrict__ out, int64_t out_stride) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double x = xyz[j], y = xyz[stride + j], z = xyz[2 * stride + j];
+    for (int ci = 0; ci < model.n_comps; ++ci) {
+        const DevComp<double>& c = model.comps[ci];
+        double theta_earth = 0.0;
+        if (c.type == D_FEATURE) theta_earth = atan2(ey - c.y0, ex - c.x0);
+        out[(int64_t)ci * out_stride + j] = density<double>(c, x - c.x0, y - c.y0, z - c.z0, theta_earth);
+    }
+}
+
 // Spline positions at n times (tests / users): earth_out, obs_out (3, n) or NULL.
 __global__ void zodi_ephemeris_positions_kernel(const __grid_constant__ LaunchArgs a, double* __restrict__ earth_out,
                                                 double* __restrict__ obs_out) {

@@ -442,6 +442,20 @@ class DeviceModel:
         del keep
         return out
 
+    def number_density(self, xyz, earth) -> np.ndarray:
+        """Number density of every component at heliocentric points ``xyz`` (3, n) [AU] for one
+        Earth position (the array part of ``grid_number_density``); returns (ncomps, n) float64."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        if xyz.ndim != 2 or xyz.shape[0] != 3:
+            raise ValueError("xyz must have shape (3, n)")
+        earth = np.ascontiguousarray(np.asarray(earth, dtype=np.float64).reshape(3))
+        n = xyz.shape[1]
+        out = np.empty((self.ncomps, n), dtype=np.float64)
+        _cabi.check(self._lib.zodi_number_density(self._handle, xyz.ctypes.data, n, max(n, 1),
+                                                  _cabi.as_double_p(earth), out.ctypes.data, max(n, 1),
+                                                  _cabi.MEM_HOST, None))
+        return out
+
     @property
     def kernel_name(self) -> str:
         return self._lib.zodi_model_kernel_name(self._handle).decode()
