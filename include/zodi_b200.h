@@ -250,6 +250,21 @@ int zodi_peer_buffer_open(int device, const uint8_t handle[ZODI_IPC_HANDLE_BYTES
 int zodi_peer_buffer_close(int device, void* ptr);
 int zodi_peer_buffer_free(int device, void* ptr);
 
+/* ---- several bands of one model in a single pass ----------------------------------------------
+ * descs[0..n_bands-1] describe the SAME Kelsall-family model (identical components, cutoffs, T_0,
+ * delta, quadrature) at different wavelengths / bandpasses: they may differ only in the blackbody
+ * table values and in emissivity / albedo / C1-C3 / solar_irradiance (what Model.__init__ derives
+ * from x, zodipy/model.py:101, zodipy/unpack_model.py:34-105).  zodi_multiband_evaluate takes the
+ * same zodi_eval_args as zodi_evaluate (u, obs, earth, flags, ephemeris, ...; return_comps is
+ * ignored) and writes the component-summed emission of band b to row b of `out`
+ * (row stride out_stride >= n): out is (n_bands, n).  Works for host and device memory. */
+#define ZODI_MAX_BANDS 16
+typedef struct zodi_multiband_s* zodi_multiband_t;
+int zodi_multiband_create(const zodi_model_desc* descs, int32_t n_bands, int device, zodi_multiband_t* out);
+int zodi_multiband_evaluate(zodi_multiband_t mb, const zodi_eval_args* args);
+int zodi_multiband_evaluate_healpix(zodi_multiband_t mb, const zodi_healpix_args* args);
+int zodi_multiband_destroy(zodi_multiband_t mb);
+
 /* ---- component densities on a set of points -------------------------------------------------
  * Replaces the array part of grid_number_density (zodipy/number_density.py:482-536): the number
  * density of every component at n heliocentric ecliptic points xyz (3, n) [AU], for one Earth

@@ -377,3 +377,44 @@ def test_grid_number_density_matches_reference_functions(name):
         np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-13 * scale, err_msg=comp["label"])
     with pytest.raises(TypeError):
         zp.grid_number_density_xyz(x, y, z, earth, model=3)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name,xs,unit", [
+    ("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um"),  # incl. scattering bands
+    ("planck18", [100.0, 143.0, 217.0, 353.0, 545.0, 857.0], "GHz"),
+    ("dirbe", [25.0, 60.0, 100.0], "um"),                                             # thermal only, NB = 4
+])
+def test_multiband_equals_per_band_models(name, xs, unit, precision):
+    """MultiBandModel == the per-band loop over single-band Models (same kernels' arithmetic up to
+    summation order), and within tolerance of the oracle; host and device memory, healpix entry."""
+    import torch
+
+    n = 6000
+    u = fibonacci_sphere(n)
+    mb = zp.MultiBandModel([zp.Quantity(x, unit) for x in xs], name=name, precision=precision)
+    got = mb.evaluate_xyz(u, EARTH_20220114)
+    assert got.shape == (len(xs), n)
+    tol, _ = TOL[precision]
+    sel = np.arange(0, n, 7)
+    for b, band in enumerate(mb.bands):
+        single = band.evaluate_xyz(u, EARTH_20220114)
+        np.testing.assert_allclose(got[b], single, rtol=1e-12 if precision == "fp64" else 3e-6)
+        ref = oracle.evaluate(band.spec, u[:, sel], EARTH_20220114, EARTH_20220114).sum(axis=0)
+        assert np.max(np.abs(got[b, sel] - ref) / np.abs(ref)) <= tol, (xs[b], precision)
+    dev = torch.device("cuda:0")
+    got_dev = mb.evaluate_xyz(torch.as_tensor(u, device=dev), torch.as_tensor(EARTH_20220114, device=dev))
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), got)
+    hp = mb.evaluate_healpix(16, EARTH_20220114)
+    assert hp.shape == (len(xs), 12 * 256)
+    np.testing.assert_allclose(hp[-1], mb.bands[-1].evaluate_healpix(16, EARTH_20220114),
+                               rtol=1e-12 if precision == "fp64" else 3e-6)
+
+
+def test_multiband_rejects_unsupported():
+    with pytest.raises(engine._cabi.ZodiError):
+        zp.MultiBandModel([zp.Quantity(25.0, "um"), zp.Quantity(60.0, "um")], name="rrm-experimental").device_model
+    with pytest.raises(ValueError):
+        zp.MultiBandModel([zp.Quantity(25.0, "um")] * 17).device_model
+    with pytest.raises(ValueError):
+        zp.MultiBandModel([zp.Quantity(25.0, "um")], weights=[None, None])

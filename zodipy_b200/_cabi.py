@@ -16,6 +16,7 @@ MAX_NODES = 1024
 MAX_TEMPS = 1024
 N_SHAPE = 8
 MAX_PEERS = 8
+MAX_BANDS = 16
 IPC_HANDLE_BYTES = 64
 
 KELSALL, RRM = 0, 1
@@ -114,6 +115,10 @@ SYMBOLS = {
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),
     "zodi_flags_from_radius": (C.c_int, [C.c_void_p, C.c_double, c_uint8_p]),
+    "zodi_multiband_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
+    "zodi_multiband_evaluate": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
+    "zodi_multiband_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
+    "zodi_multiband_destroy": (C.c_int, [C.c_void_p]),
     "zodi_number_density": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
                                       C.c_int64, C.c_int32, C.c_void_p]),
     "zodi_peer_buffer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), c_uint8_p]),

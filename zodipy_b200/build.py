@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libzodi_b200.so")
 SOURCES = ["zodi_capi.cu"]
-HEADERS = ["zodi_device.cuh", "zodi_fp64_tables.cuh", "zodi_kernels.cuh", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh", "zodi_model_build.hpp", os.path.join("..", "..", "include", "zodi_b200.h")]
+HEADERS = ["zodi_device.cuh", "zodi_fp64_tables.cuh", "zodi_kernels.cuh", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh", "zodi_multiband.cuh", "zodi_model_build.hpp", os.path.join("..", "..", "include", "zodi_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -74,6 +74,12 @@ struct zodi_model_s {
     bool kelsall_ok = false;  // model fits the fused Kelsall-family kernel
     KelsallModel<double> k64;
     KelsallModel<float> k32;
+    // multi-band extension (zodi_multiband_*): this handle then carries band 0 and the shared parts
+    int mb_bands = 0;
+    MultiBandModel<double> mb64;
+    MultiBandModel<float> mb32;
+    Pair<double>* d_mbtab64 = nullptr;  // [n_bands][n_temps]
+    Pair<float>* d_mbtab32 = nullptr;
     int force_generic = 0;    // testing knob (ZODI_FORCE_GENERIC=1): always use the generic kernel
     int no_x2 = 0;            // testing knob (ZODI_NO_X2=1): scalar fused kernel instead of packed
     Pair<double>* d_table64 = nullptr;
@@ -270,8 +276,33 @@ cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a,
     return cudaGetLastError();
 }
 
+template <typename Real, int NB>
+cudaError_t launch_multiband_NB(const MultiBandModel<Real>& MB, const LaunchArgs& a, const Pair<Real>* tabs,
+                                const Pair<Real>* nodes, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((a.n + kThreads - 1) / kThreads);
+    const bool rf = MB.base.n_comps == 6, sc = MB.base.scatter != 0;
+    if (rf && sc) zodi_los_multiband_kernel<Real, NB, true, true><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
+    else if (rf) zodi_los_multiband_kernel<Real, NB, true, false><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
+    else if (sc) zodi_los_multiband_kernel<Real, NB, false, true><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
+    else zodi_los_multiband_kernel<Real, NB, false, false><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <typename Real>
+cudaError_t launch_multiband(const MultiBandModel<Real>& MB, const LaunchArgs& a, const Pair<Real>* tabs,
+                             const Pair<Real>* nodes, cudaStream_t stream) {
+    if (MB.n_bands <= 4) return launch_multiband_NB<Real, 4>(MB, a, tabs, nodes, stream);
+    if (MB.n_bands <= 8) return launch_multiband_NB<Real, 8>(MB, a, tabs, nodes, stream);
+    return launch_multiband_NB<Real, 16>(MB, a, tabs, nodes, stream);
+}
+
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
+    if (m->mb_bands > 0) {
+        if (precision == ZODI_FP32) return launch_multiband<float>(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+        return launch_multiband<double>(m->mb64, a, m->d_mbtab64, m->d_nodes64, stream);
+    }
     if (m->kelsall_ok && !m->force_generic) {
         // packed-fp32 kernel: fp32, thermal-only, enough lines of sight for thread-per-pair mapping
         if (precision == ZODI_FP32 && !m->k32.scatter && !m->no_x2 &&
@@ -370,7 +401,7 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
     if ((need_u && a->u_stride < a->n) || a->obs_stride < a->n_obs || a->earth_stride < a->n_earth)
         return fail(ZODI_ERR_INVALID, "row strides must be >= row lengths");
 positions_checked:
-    if (a->return_comps && a->n_peers == 0 && a->out_stride < a->n)
+    if ((a->return_comps || m->mb_bands > 0) && a->n_peers == 0 && a->out_stride < a->n)
         return fail(ZODI_ERR_INVALID, "out_stride=%lld < n", (long long)a->out_stride);
     if (a->precision != ZODI_FP64 && a->precision != ZODI_FP32)
         return fail(ZODI_ERR_INVALID, "unknown precision %d", a->precision);
@@ -426,7 +457,8 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
     if (rc) return rc;
     chunk = std::min<int64_t>(m->ws_chunk, std::max<int64_t>(chunk, 1));
     const size_t osz = a->out_dtype == ZODI_OUT_F32 ? sizeof(float) : sizeof(double);
-    const int out_rows = a->return_comps ? m->desc.n_comps : 1;
+    const int out_rows = m->mb_bands > 0 ? m->mb_bands : (a->return_comps ? m->desc.n_comps : 1);
+    const bool rows_out = m->mb_bands > 0 || a->return_comps;
     const bool obs_ps = !a->ephemeris && a->n_obs == n && n > 1;
     const bool earth_ps = !a->ephemeris && a->n_earth == n && n > 1;
     for (Slot& s : m->slots) s.used = false;
@@ -475,7 +507,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         CU_CHECK(cudaEventRecord(s.k1, s.stream));
         s.used = true;
         CU_CHECK(cudaMemcpy2DAsync((char*)a->out + (size_t)done * osz,
-                                   (size_t)(a->return_comps ? a->out_stride : n) * osz, s.d_out,
+                                   (size_t)(rows_out ? a->out_stride : n) * osz, s.d_out,
                                    (size_t)m->ws_chunk * osz, (size_t)cn * osz, out_rows,
                                    cudaMemcpyDeviceToHost, s.stream));
         done += cn;
@@ -554,6 +586,7 @@ int zodi_model_destroy(zodi_model_t m) {
         cudaFree(m->d_table64); cudaFree(m->d_nodes64);
         cudaFree(m->d_table32); cudaFree(m->d_nodes32);
         cudaFree(m->d_scratch);
+        cudaFree(m->d_mbtab64); cudaFree(m->d_mbtab32);
     }
     delete m;
     return ZODI_OK;
@@ -819,6 +852,105 @@ int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_s
                          (size_t)n * sizeof(double), 3, cudaMemcpyDeviceToHost);
     if (memory == ZODI_MEM_HOST) cudaFree(d_out);
     if (e != cudaSuccess) return fail(ZODI_ERR_CUDA, "healpix vectors failed: %s", cudaGetErrorString(e));
+    return ZODI_OK;
+}
+
+// ---- multi-band ------------------------------------------------------------------------------
+struct zodi_multiband_s { zodi_model_s* model; };
+
+static bool same_geometry(const zodi_model_desc& a, const zodi_model_desc& b) {
+    if (a.kind != b.kind || a.n_comps != b.n_comps || a.n_nodes != b.n_nodes || a.n_temps != b.n_temps) return false;
+    if (a.T_0 != b.T_0 || a.delta != b.delta) return false;
+    for (int i = 0; i < a.n_temps; ++i) if (a.temps[i] != b.temps[i]) return false;
+    for (int i = 0; i < a.n_nodes; ++i) if (a.nodes[i] != b.nodes[i] || a.weights[i] != b.weights[i]) return false;
+    for (int c = 0; c < a.n_comps; ++c) {
+        const zodi_component_desc &p = a.comps[c], &q = b.comps[c];
+        if (p.type != q.type || p.cutoff_inner != q.cutoff_inner || p.cutoff_outer != q.cutoff_outer) return false;
+        if (std::memcmp(p.x0, q.x0, sizeof(p.x0)) || std::memcmp(p.shape, q.shape, sizeof(p.shape))) return false;
+        if (p.sin_Omega != q.sin_Omega || p.cos_Omega != q.cos_Omega || p.sin_i != q.sin_i || p.cos_i != q.cos_i) return false;
+    }
+    return true;
+}
+
+int zodi_multiband_create(const zodi_model_desc* descs, int32_t n_bands, int device, zodi_multiband_t* out) {
+    if (!out) return fail(ZODI_ERR_INVALID, "out handle pointer is NULL");
+    *out = nullptr;
+    if (!descs || n_bands < 1 || n_bands > ZODI_MAX_BANDS)
+        return fail(ZODI_ERR_INVALID, "n_bands=%d outside [1, %d]", n_bands, ZODI_MAX_BANDS);
+    static_assert(ZODI_MAX_BANDS == kMaxBands, "band capacity");
+    for (int b = 0; b < n_bands; ++b) {
+        int rc = validate_desc(&descs[b]);
+        if (rc) return rc;
+        if (!same_geometry(descs[0], descs[b]))
+            return fail(ZODI_ERR_INVALID, "band %d differs from band 0 in more than its spectral parameters", b);
+    }
+    zodi_model_t m = nullptr;
+    int rc = zodi_model_create(&descs[0], device, &m);
+    if (rc) return rc;
+    if (!m->kelsall_ok) {
+        zodi_model_destroy(m);
+        return fail(ZODI_ERR_UNSUPPORTED, "multi-band evaluation needs a Kelsall-family model layout");
+    }
+    DeviceGuard guard(device);
+    MultiBandModel<double>& MB = m->mb64;
+    std::memset(&MB, 0, sizeof(MB));
+    MB.base = m->k64;
+    MB.n_bands = n_bands;
+    MB.n_bands_padded = n_bands <= 4 ? 4 : (n_bands <= 8 ? 8 : 16);
+    const int nt = descs[0].n_temps;
+    std::vector<Pair<double>> t64((size_t)n_bands * nt);
+    std::vector<Pair<float>> t32((size_t)n_bands * nt);
+    for (int b = 0; b < n_bands; ++b) {
+        KelsallModel<double> kb;
+        if (!build_kelsall_model(descs[b], kb)) {
+            zodi_model_destroy(m);
+            return fail(ZODI_ERR_UNSUPPORTED, "band %d is not eligible for the fused kernel", b);
+        }
+        for (int c = 0; c < 6; ++c) { MB.aB[b][c] = kb.aB[c]; MB.aS[b][c] = kb.aS[c]; }
+        MB.C1p[b] = kb.C1p; MB.C2p[b] = kb.C2p; MB.C3l[b] = kb.C3l;
+        if (kb.scatter) MB.base.scatter = 1;
+        std::vector<Pair<double>> tb, nb;
+        std::vector<Pair<float>> tbf, nbf;
+        build_pairs(descs[b], tb, nb, tbf, nbf);
+        for (int i = 0; i < nt; ++i) { t64[(size_t)b * nt + i] = tb[i]; t32[(size_t)b * nt + i] = tbf[i]; }
+    }
+    MultiBandModel<float>& MF = m->mb32;
+    std::memset(&MF, 0, sizeof(MF));
+    narrow_kelsall(MB.base, MF.base);
+    MF.n_bands = MB.n_bands; MF.n_bands_padded = MB.n_bands_padded;
+    for (int b = 0; b < kMaxBands; ++b) {
+        for (int c = 0; c < 6; ++c) { MF.aB[b][c] = (float)MB.aB[b][c]; MF.aS[b][c] = (float)MB.aS[b][c]; }
+        MF.C1p[b] = (float)MB.C1p[b]; MF.C2p[b] = (float)MB.C2p[b]; MF.C3l[b] = (float)MB.C3l[b];
+    }
+    cudaError_t e = cudaMalloc((void**)&m->d_mbtab64, t64.size() * sizeof(Pair<double>));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_mbtab64, t64.data(), t64.size() * sizeof(Pair<double>), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_mbtab32, t32.size() * sizeof(Pair<float>));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_mbtab32, t32.data(), t32.size() * sizeof(Pair<float>), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        zodi_model_destroy(m);
+        return fail(ZODI_ERR_CUDA, "multi-band table upload failed: %s", cudaGetErrorString(e));
+    }
+    m->mb_bands = n_bands;
+    zodi_multiband_s* h = new (std::nothrow) zodi_multiband_s{m};
+    if (!h) { zodi_model_destroy(m); return fail(ZODI_ERR_NOMEM, "out of host memory"); }
+    *out = h;
+    return ZODI_OK;
+}
+
+int zodi_multiband_evaluate(zodi_multiband_t mb, const zodi_eval_args* a) {
+    if (!mb) return fail(ZODI_ERR_INVALID, "multi-band handle is NULL");
+    return evaluate_impl(mb->model, a, nullptr);
+}
+
+int zodi_multiband_evaluate_healpix(zodi_multiband_t mb, const zodi_healpix_args* hp) {
+    if (!mb) return fail(ZODI_ERR_INVALID, "multi-band handle is NULL");
+    return zodi_evaluate_healpix(mb->model, hp);
+}
+
+int zodi_multiband_destroy(zodi_multiband_t mb) {
+    if (!mb) return ZODI_OK;
+    zodi_model_destroy(mb->model);
+    delete mb;
     return ZODI_OK;
 }
 

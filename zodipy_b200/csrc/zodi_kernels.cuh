@@ -13,6 +13,7 @@
 #include "zodi_device.cuh"
 #include "zodi_kelsall.cuh"
 #include "zodi_kelsall_x2.cuh"
+#include "zodi_multiband.cuh"
 
 namespace zodi {
 
@@ -267,6 +268,37 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
         if (act0) store_out<float>(args, 0, j0, tot0);
         if (act1) store_out<float>(args, 0, j1, tot1);
     }
+}
+
+// Multi-band kernel (zodi_multiband.cuh): NB bands of one Kelsall-family model per pass; output
+// row b of `out` (row stride out_stride) is band b's component-summed emission.
+template <typename Real, int NB, bool HAS_RF, bool SCATTER>
+__global__ void __launch_bounds__(kThreads)
+zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
+                          const __grid_constant__ LaunchArgs args,
+                          const Pair<Real>* __restrict__ g_tables,   // [n_bands][n_temps]
+                          const Pair<Real>* __restrict__ g_nodes) {
+    __shared__ Pair<Real> s_tables[NB * kFastMaxTemps];
+    __shared__ Pair<Real> s_nodes[kFastMaxNodes];
+    const int nt = model.base.n_temps;
+    for (int i = threadIdx.x; i < NB * nt; i += blockDim.x) {
+        const Pair<Real> zero = {Real(0), Real(0)};
+        s_tables[i] = (i < model.n_bands * nt) ? g_tables[i] : zero;  // padded bands: zero source
+    }
+    for (int i = threadIdx.x; i < model.base.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = j < args.n;
+    const int64_t jj = active ? j : args.n - 1;
+    double ux, uy, uz, ox, oy, oz, ex, ey;
+    load_direction(args, jj, ux, uy, uz);
+    load_positions(args, jj, HAS_RF, ox, oy, oz, ex, ey);
+    integrate_kelsall_multiband<Real, NB, HAS_RF, SCATTER>(
+        model, s_tables, s_nodes, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, 0, 1,
+        [&](int b, Real v) {
+            if (active && b < model.n_bands) store_out<Real>(args, b, j, v);
+        });
 }
 
 // Pixel-centre unit vectors only (same device routine the integrator uses in its prologue).

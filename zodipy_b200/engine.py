@@ -468,6 +468,54 @@ class DeviceModel:
         return float(self._lib.zodi_last_kernel_ms(self._handle))
 
 
+class DeviceMultiBand(DeviceModel):
+    """Several bands of ONE Kelsall-family model evaluated in a single pass (shared geometry,
+    temperature, table index and densities; per band one table read and a weighted sum).
+
+    ``specs``: one neutral spec per band (``zodipy_b200.spec.build_spec`` of the same model at each
+    wavelength / bandpass).  The evaluate calls of :class:`DeviceModel` apply unchanged and return
+    the component-summed emission per band, shape (n_bands, N); ``return_comps`` is not available.
+    """
+
+    def __init__(self, specs, device: int = 0):
+        self._lib = _cabi.load()
+        if not 1 <= len(specs) <= _cabi.MAX_BANDS:
+            raise ValueError(f"number of bands must be in [1, {_cabi.MAX_BANDS}]")
+        self.spec = specs[0]
+        self.specs = list(specs)
+        self.device = int(device)
+        self.n_bands = len(specs)
+        self.ncomps = self.n_bands  # rows of the output
+        descs = (_cabi.ModelDesc * self.n_bands)()
+        keep = []
+        for i, sp in enumerate(specs):
+            d, k = pack_desc(sp)
+            descs[i] = d
+            keep.append(k)
+        self._mb = C.c_void_p()
+        _cabi.check(self._lib.zodi_multiband_create(descs, self.n_bands, self.device, C.byref(self._mb)))
+        del keep
+        # the multi-band handle wraps a model handle as its first member
+        self._handle = C.c_void_p(C.cast(self._mb, C.POINTER(C.c_void_p))[0])
+
+    def update(self, spec):
+        raise NotImplementedError("rebuild the DeviceMultiBand after a parameter update")
+
+    def close(self) -> None:
+        if getattr(self, "_mb", None) is not None and self._mb.value:
+            self._lib.zodi_multiband_destroy(self._mb)
+            self._mb = C.c_void_p()
+            self._handle = C.c_void_p()
+
+    def evaluate(self, u, obs=None, earth=None, **kwargs):
+        kwargs.pop("return_comps", None)
+        return super().evaluate(u, obs, earth, return_comps=True, **kwargs)
+
+    def evaluate_healpix(self, nside, obs, earth=None, **kwargs):
+        kwargs.pop("return_comps", None)
+        return super().evaluate_healpix(nside, obs, earth, return_comps=True, **kwargs)
+
+
 def kernel_launch_count() -> int:
     return int(_cabi.load().zodi_kernel_launch_count())
 

@@ -199,3 +199,61 @@ class Model:
                 new[key] = {ComponentLabel(k): v for k, v in value.items()}
         self._ipd_model = self._ipd_model.__class__(**new)
         self._init_ipd_model_partials()
+
+
+class MultiBandModel:
+    """Several wavelengths / bandpasses of ONE model evaluated in a single pass over the lines of
+    sight (additive API).
+
+    ``xs``: sequence of Quantities (scalars or bandpass arrays), ``weights``: matching sequence of
+    bandpass weights or ``None`` entries.  Equivalent to ``[Model(x, weights=w, name=name, ...)
+    .evaluate_xyz(...) for x, w in zip(xs, weights)]`` - the per-band loop of the reference's own
+    tests (tests/test_evaluate.py:54-66) - but positions, temperatures and number densities are
+    computed once and shared by all bands.  Returns the component-summed emission, shape
+    (n_bands, N).  Kelsall-family models (dirbe, planck13/15/18, odegard), up to 16 bands.
+    """
+
+    def __init__(self, xs, *, weights=None, name: str = "dirbe", gauss_quad_degree: int = 50,
+                 extrapolate: bool = False, precision: str = "fp64", device: int | None = None) -> None:
+        xs = list(xs)
+        weights = [None] * len(xs) if weights is None else list(weights)
+        if len(weights) != len(xs):
+            raise ValueError("weights must have one entry (array or None) per band")
+        # one single-band Model per band does validation, bandpass normalisation and unpacking
+        self.bands = [Model(x, weights=w, name=name, gauss_quad_degree=gauss_quad_degree,
+                            extrapolate=extrapolate, precision=precision, device=device)
+                      for x, w in zip(xs, weights)]
+        self._precision = precision
+        self._device = self.bands[0]._device
+        self._device_model = None
+
+    @property
+    def n_bands(self) -> int:
+        return len(self.bands)
+
+    @property
+    def specs(self) -> list:
+        return [m.spec for m in self.bands]
+
+    @property
+    def device_model(self):
+        from .engine import DeviceMultiBand
+
+        if self._device_model is None:
+            self._device_model = DeviceMultiBand(self.specs, self._device)
+        return self._device_model
+
+    def evaluate_xyz(self, unit_vectors, obs_xyz, earth_xyz=None, *, precision: str | None = None, out=None,
+                     out_dtype=None, outside_flags=None):
+        """(n_bands, N) emission [MJy/sr] for ecliptic unit vectors (3, N); see ``Model.evaluate_xyz``."""
+        return self.device_model.evaluate(unit_vectors, obs_xyz, earth_xyz,
+                                          precision=precision or self._precision, out=out,
+                                          out_dtype=out_dtype, outside_flags=outside_flags)
+
+    def evaluate_healpix(self, nside: int, obs_xyz, earth_xyz=None, *, frame_rotation=None, pix_range=None,
+                         nest: bool = False, precision: str | None = None, out=None, out_dtype=None,
+                         device_out: bool = False):
+        """(n_bands, npix) HEALPix maps with on-device directions; see ``Model.evaluate_healpix``."""
+        return self.device_model.evaluate_healpix(
+            nside, obs_xyz, earth_xyz, pix_range=pix_range, rot=frame_rotation, nest=nest,
+            precision=precision or self._precision, out=out, out_dtype=out_dtype, device_out=device_out)
