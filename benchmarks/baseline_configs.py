@@ -138,6 +138,41 @@ def tod_e2e(dev, n=20_000_000):
     print(json.dumps(res), flush=True)
 
 
+def multiband(dev):
+    """All bands of a model for the same pointings: MultiBandModel vs the per-band loop."""
+    for name, xs, unit, nside in (("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um", 512),
+                                  ("planck18", [100.0, 143.0, 217.0, 353.0, 545.0, 857.0], "GHz", 1024)):
+        u = healpix_dirs(nside, dev)
+        earth = torch.as_tensor(EARTH, device=dev)
+        mb = zp.MultiBandModel([zp.Quantity(x, unit) for x in xs], name=name, precision="fp32")
+        res = {"config": f"multiband: {name} {len(xs)} bands nside={nside}", "n_los": u.shape[1], "n_bands": len(xs)}
+        out = mb.evaluate_xyz(u, earth, out_dtype=np.float32)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            mb.evaluate_xyz(u, earth, out=out, out_dtype=np.float32)
+        b.record()
+        torch.cuda.synchronize()
+        ms_mb = a.elapsed_time(b) / 5
+        singles = [torch.empty(u.shape[1], dtype=torch.float32, device=dev) for _ in xs]
+        for m, o in zip(mb.bands, singles):
+            m.evaluate_xyz(u, earth, out=o, out_dtype=np.float32)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            for m, o in zip(mb.bands, singles):
+                m.evaluate_xyz(u, earth, out=o, out_dtype=np.float32)
+        b.record()
+        torch.cuda.synchronize()
+        ms_loop = a.elapsed_time(b) / 5
+        diff = max(float(((out[i] - singles[i]).abs() / singles[i].abs()).max()) for i in range(len(xs)))
+        band_evals = u.shape[1] * mb.bands[0].ncomps * 50 * len(xs)
+        res.update({"multiband_ms": ms_mb, "per_band_loop_ms": ms_loop, "speedup": ms_loop / ms_mb,
+                    "band_evals_per_s": band_evals / (ms_mb * 1e-3), "max_rel_diff_vs_single_band": diff})
+        print(json.dumps(res), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-n", type=float, default=2.1e8)
@@ -164,6 +199,7 @@ def main():
         run("5: planck13 545GHz nside=4096", zp.Model(Q(545.0, "GHz"), name="planck13"), healpix_dirs(4096, dev),
             earth, earth, 3e8)
     tod_e2e(dev)
+    multiband(dev)
     # extra: scattering branch and the generic kernel (RRM)
     run("extra: dirbe 1.25um (scattering) nside=512", zp.Model(Q(1.25, "um")), healpix_dirs(512, dev), earth, earth,
         args.skip_fp64_above)
