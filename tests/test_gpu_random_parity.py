@@ -1,0 +1,59 @@
+"""Randomised parity sweep: CUDA path vs oracle for random models, wavelengths, observers,
+quadrature degrees and pointing sets (seeded; complements the fixed fixtures).  The reference's own
+property tests (tests/test_evaluate.py:69-95) only assert shapes; here the values are compared."""
+import numpy as np
+import pytest
+
+import zodi_oracle as oracle
+import zodipy_b200 as zp
+from helpers import COMP_FLOOR_FP32, COMP_FLOOR_FP64, TOL_FP32, TOL_FP64, max_rel_comps, max_rel_total
+
+pytestmark = pytest.mark.gpu
+
+MODELS = {"dirbe": ("um", 1.25, 240.0), "planck13": ("GHz", 100.0, 857.0), "planck15": ("GHz", 100.0, 857.0),
+          "planck18": ("GHz", 100.0, 857.0), "odegard": ("GHz", 100.0, 857.0),
+          "rrm-experimental": ("um", 12.0, 100.0)}
+
+
+def _case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    name = list(MODELS)[seed % len(MODELS)]
+    unit, lo, hi = MODELS[name]
+    if rng.random() < 0.3:  # bandpass
+        centre = np.exp(rng.uniform(np.log(lo * 1.2), np.log(hi / 1.2)))
+        x = np.linspace(centre / 1.15, centre * 1.15, int(rng.integers(5, 30)))
+        x = x[(x >= lo) & (x <= hi)]
+        w = np.exp(-0.5 * ((x - centre) / (0.08 * centre)) ** 2) + 0.05
+        model_args = dict(x=zp.Quantity(x, unit), weights=w)
+    else:
+        model_args = dict(x=zp.Quantity(float(np.exp(rng.uniform(np.log(lo), np.log(hi)))), unit))
+    deg = int(rng.choice([5, 11, 32, 50, 50, 50, 64, 101, 150]))
+    n = int(rng.integers(200, 3000))
+    u = rng.normal(size=(3, n))
+    u /= np.linalg.norm(u, axis=0)
+    r_obs = float(np.exp(rng.uniform(np.log(0.3), np.log(4.0))))
+    lon = rng.uniform(0, 2 * np.pi)
+    base = r_obs * np.array([np.cos(lon), np.sin(lon), rng.uniform(-0.05, 0.05)])
+    earth0 = np.array([np.cos(lon + 0.3), np.sin(lon + 0.3), 0.0])
+    if rng.random() < 0.4:  # time-ordered: per-sample observer / Earth
+        ang = np.linspace(0, rng.uniform(0.05, 1.5), n)
+        rot = lambda v: np.array([v[0] * np.cos(ang) - v[1] * np.sin(ang), v[0] * np.sin(ang) + v[1] * np.cos(ang),
+                                  v[2] + 0 * ang])  # noqa: E731
+        obs, earth = rot(base) * (1 + 0.01 * np.sin(7 * ang)), rot(earth0)
+    else:
+        obs, earth = base.reshape(3, 1), earth0.reshape(3, 1)
+    return name, model_args, deg, u, np.ascontiguousarray(obs), np.ascontiguousarray(earth)
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_configuration(seed):
+    name, model_args, deg, u, obs, earth = _case(seed)
+    ref = None
+    for precision, tol, floor in (("fp64", TOL_FP64, COMP_FLOOR_FP64), ("fp32", TOL_FP32, COMP_FLOOR_FP32)):
+        model = zp.Model(name=name, gauss_quad_degree=deg, precision=precision, **model_args)
+        if ref is None:
+            ref = oracle.evaluate(model.spec, u, obs, earth)
+        got = model.evaluate_xyz(u, obs, earth, return_comps=True)
+        info = (seed, name, precision, deg, float(np.linalg.norm(obs[:, 0])))
+        assert max_rel_total(got, ref) <= tol, info
+        assert max_rel_comps(got, ref, floor=floor) <= tol, info
