@@ -175,6 +175,12 @@ def density_cloud(X, p, earth=None):  # number_density.py:47-73
     return p["n_0"] * Rc ** -p["alpha"] * np.exp(-p["beta"] * g ** p["gamma"])
 
 
+# Test aid: evaluate the band's radial cut-off as -expm1(-x) instead of the reference's literal
+# 1 - exp(-x).  The difference between the two oracle runs is the reference's OWN cancellation
+# noise (relative eps / x for x = (R/delta_r)**20 << 1), which tests use as an error allowance.
+BAND_RADIAL_EXPM1 = False
+
+
 def density_band(X, p, earth=None):  # number_density.py:76-110
     _, Rc, Zc = _plane_geometry(X, p)
     zeta = np.abs(Zc / Rc)
@@ -182,8 +188,22 @@ def density_band(X, p, earth=None):  # number_density.py:76-110
     t1 = 3 * p["n_0"] / Rc
     t2 = np.exp(-(s**6))
     t3 = 1 + (s ** p["p"]) / p["v"]
-    t4 = 1 - np.exp(-((Rc / p["delta_r"]) ** 20))
+    x20 = (Rc / p["delta_r"]) ** 20
+    t4 = -np.expm1(-x20) if BAND_RADIAL_EXPM1 else 1 - np.exp(-x20)
     return t1 * t2 * t3 * t4
+
+
+def reference_rounding_noise(spec, u, obs, earth):
+    """|literal - cancellation-free| per component and line of sight: how far the reference's own
+    result is from the exactly rounded value of its formula because of 1 - exp(-x) (Q9)."""
+    global BAND_RADIAL_EXPM1
+    literal = evaluate(spec, u, obs, earth)
+    BAND_RADIAL_EXPM1 = True
+    try:
+        accurate = evaluate(spec, u, obs, earth)
+    finally:
+        BAND_RADIAL_EXPM1 = False
+    return np.abs(literal - accurate)
 
 
 def density_ring(X, p, earth=None):  # number_density.py:113-139
