@@ -55,7 +55,13 @@ def test_random_configuration(seed):
             ref = oracle.evaluate(model.spec, u, obs, earth)
         got = model.evaluate_xyz(u, obs, earth, return_comps=True)
         info = (seed, name, precision, deg, float(np.linalg.norm(obs[:, 0])))
-        assert max_rel_total(got, ref) <= tol, info
+        # totals relative to sum_c |component|: identical to |total| for the usual all-positive models,
+        # but planck13's partly NEGATIVE emissivities (source_params.py:43,47-48) let components cancel,
+        # so the total can pass through zero and its own relative error is unbounded
+        l1 = np.abs(ref).sum(axis=0)
+        assert np.nanmax(np.abs(got.sum(axis=0) - ref.sum(axis=0)) / l1) <= tol, info
+        if name != "planck13":
+            assert max_rel_total(got, ref) <= tol, info
         if precision == "fp64" and noise is None:
             # observers inside ~0.8 delta_r: the reference's literal 1 - exp(-(R/delta_r)^20) carries
             # cancellation noise far above 1e-10 on the band components; allow that noise bound
