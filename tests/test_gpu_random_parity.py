@@ -47,6 +47,28 @@ def _case(seed):
     return name, model_args, deg, u, np.ascontiguousarray(obs), np.ascontiguousarray(earth)
 
 
+def _near_hard_cutoff(spec, u, obs, margin=1e-6):
+    """Lines of sight with a quadrature node within `margin` AU of a hard density cut-off
+    (R_inner / R_outer of the RRM fan, comet and bands, number_density.py:201-203,239-241,...).
+    The reference decides `R <= R_outer` in float64; an fp32 kernel cannot classify a node that
+    close to the discontinuity the same way, so those rays are excluded from the fp32 comparison.
+    They only occur because the reference's range formula (no z-term, quirk Q2) lets rays of
+    observers far off the ecliptic overshoot the cut-off sphere."""
+    bad = np.zeros(u.shape[1], dtype=bool)
+    start, stop = oracle.los_range(spec, u, obs)
+    for ci, comp in enumerate(spec["comps"]):
+        bounds = [comp["params"][k] for k in ("R_inner", "R_outer") if k in comp["params"]]
+        if not bounds:
+            continue
+        x0 = np.asarray(comp["params"]["X_0"]).reshape(3, 1)
+        for r in spec["points"]:
+            R_los = 0.5 * (stop[ci] - start[ci]) * r + 0.5 * (stop[ci] + start[ci])
+            R = np.sqrt(((R_los * u + obs - x0) ** 2).sum(axis=0))
+            for b in bounds:
+                bad |= np.abs(R - b) < margin
+    return bad
+
+
 N_SEEDS = int(os.environ.get("ZODI_SWEEP_SEEDS", "36"))  # raise for a wider one-off hunt
 
 
@@ -59,18 +81,24 @@ def test_random_configuration(seed):
         if ref is None:
             ref = oracle.evaluate(model.spec, u, obs, earth)
         got = model.evaluate_xyz(u, obs, earth, return_comps=True)
+        if precision == "fp32" and model.spec["kind"] == "rrm":
+            keep = ~_near_hard_cutoff(model.spec, u, obs)
+            assert keep.mean() > 0.99
+            got, ref_p = got[:, keep], ref[:, keep]
+        else:
+            ref_p = ref
         info = (seed, name, precision, deg, float(np.linalg.norm(obs[:, 0])))
         # totals relative to sum_c |component|: identical to |total| for the usual all-positive models,
         # but planck13's partly NEGATIVE emissivities (source_params.py:43,47-48) let components cancel,
         # so the total can pass through zero and its own relative error is unbounded
-        l1 = np.abs(ref).sum(axis=0)
-        assert np.nanmax(np.abs(got.sum(axis=0) - ref.sum(axis=0)) / l1) <= tol, info
+        l1 = np.abs(ref_p).sum(axis=0)
+        assert np.nanmax(np.abs(got.sum(axis=0) - ref_p.sum(axis=0)) / l1) <= tol, info
         if name != "planck13":
-            assert max_rel_total(got, ref) <= tol, info
+            assert max_rel_total(got, ref_p) <= tol, info
         if precision == "fp64" and noise is None:
             # observers inside ~0.8 delta_r: the reference's literal 1 - exp(-(R/delta_r)^20) carries
             # cancellation noise far above 1e-10 on the band components; allow that noise bound
             noise = oracle.reference_rounding_noise(model.spec, u, obs, earth)
         allowance = noise if precision == "fp64" else 0.0
-        scale = np.maximum(np.abs(ref), floor * np.abs(ref.sum(axis=0))[None, :])
-        assert np.nanmax((np.abs(got - ref) - allowance) / scale) <= tol, info
+        scale = np.maximum(np.abs(ref_p), floor * np.abs(ref_p.sum(axis=0))[None, :])
+        assert np.nanmax((np.abs(got - ref_p) - allowance) / scale) <= tol, info
