@@ -83,7 +83,7 @@ def test_random_configuration(seed):
         got = model.evaluate_xyz(u, obs, earth, return_comps=True)
         if precision == "fp32" and model.spec["kind"] == "rrm":
             keep = ~_near_hard_cutoff(model.spec, u, obs)
-            assert keep.mean() > 0.99
+            assert keep.mean() > 0.9  # Gauss-Legendre nodes crowd towards the ends of the range at high degree
             got, ref_p = got[:, keep], ref[:, keep]
         else:
             ref_p = ref
