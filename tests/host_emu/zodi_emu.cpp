@@ -87,12 +87,16 @@ static void run_kelsall_x2(const KelsallModel<float>& K, const std::vector<Pair<
             ey[q] = earth[n_earth + je];
         }
         auto emit2 = [&](int ci, float a, float b) { out[ci * n + jj[0]] = a; out[ci * n + jj[1]] = b; };
-        if (K.share13) kelsall_group_a_x2<true>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2);
-        else kelsall_group_a_x2<false>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2);
+#define ZX2(SH, SC) kelsall_group_a_x2<SH, SC>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2)
+        if (K.share13) { if (K.scatter) ZX2(true, true); else ZX2(true, false); }
+        else { if (K.scatter) ZX2(false, true); else ZX2(false, false); }
+#undef ZX2
         if (K.n_comps == 6)
-            for (int q = 1; q >= 0; --q)
-                kelsall_ring_feature_packed(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask,
-                                            [&](float r, float f) { out[4 * n + jj[q]] = r; out[5 * n + jj[q]] = f; });
+            for (int q = 1; q >= 0; --q) {
+                auto put = [&](float r, float f) { out[4 * n + jj[q]] = r; out[5 * n + jj[q]] = f; };
+                if (K.scatter) kelsall_ring_feature_packed<true>(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask, put);
+                else kelsall_ring_feature_packed<false>(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask, put);
+            }
     }
 }
 
@@ -134,7 +138,7 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
     if (precision == ZODI_FP32) {
         KelsallModel<float> k32;
         narrow_kelsall(k64, k32);
-        if (fast == 2 && !k32.scatter) {
+        if (fast == 2) {
             run_kelsall_x2(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out);
             return 2;
         }

@@ -264,16 +264,24 @@ cudaError_t launch_kelsall(const KelsallModel<Real>& K, const LaunchArgs& a, con
     return launch_kelsall_RS<Real, false, false>(K, a, tab, nodes, stream);
 }
 
-template <bool HAS_RF, bool SHARE13>
+template <bool HAS_RF, bool SHARE13, bool SCATTER>
 cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
                               const Pair<float>* nodes, cudaStream_t stream) {
     const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
     // cloud+bands only: 5 CTAs/SM (48 registers) measured 5 % faster than 4 CTAs/SM (60 registers)
-    // on B200; with the ring/feature loops 48 registers spill, so that variant keeps 4 CTAs/SM.
-    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, HAS_RF ? 4 : 5>
+    // on B200; the ring/feature loops and the scattering terms need more registers (4 / 3 CTAs/SM).
+    constexpr int kMinCtas = SCATTER ? 3 : (HAS_RF ? 4 : 5);
+    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, kMinCtas>
         <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+template <bool HAS_RF, bool SHARE13>
+cudaError_t launch_kelsall_x2_S(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
+                                const Pair<float>* nodes, cudaStream_t stream) {
+    return K.scatter ? launch_kelsall_x2<HAS_RF, SHARE13, true>(K, a, tab, nodes, stream)
+                     : launch_kelsall_x2<HAS_RF, SHARE13, false>(K, a, tab, nodes, stream);
 }
 
 template <typename Real, int NB>
@@ -305,14 +313,13 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
     }
     if (m->kelsall_ok && !m->force_generic) {
         // packed-fp32 kernel: fp32, thermal-only, enough lines of sight for thread-per-pair mapping
-        if (precision == ZODI_FP32 && !m->k32.scatter && !m->no_x2 &&
-            pick_lanes(a.n / 2, m->k32.n_nodes) == 1) {
+        if (precision == ZODI_FP32 && !m->no_x2 && pick_lanes(a.n / 2, m->k32.n_nodes) == 1) {
             const KelsallModel<float>& K = m->k32;
             if (K.n_comps == 6)
-                return K.share13 ? launch_kelsall_x2<true, true>(K, a, m->d_table32, m->d_nodes32, stream)
-                                 : launch_kelsall_x2<true, false>(K, a, m->d_table32, m->d_nodes32, stream);
-            return K.share13 ? launch_kelsall_x2<false, true>(K, a, m->d_table32, m->d_nodes32, stream)
-                             : launch_kelsall_x2<false, false>(K, a, m->d_table32, m->d_nodes32, stream);
+                return K.share13 ? launch_kelsall_x2_S<true, true>(K, a, m->d_table32, m->d_nodes32, stream)
+                                 : launch_kelsall_x2_S<true, false>(K, a, m->d_table32, m->d_nodes32, stream);
+            return K.share13 ? launch_kelsall_x2_S<false, true>(K, a, m->d_table32, m->d_nodes32, stream)
+                             : launch_kelsall_x2_S<false, false>(K, a, m->d_table32, m->d_nodes32, stream);
         }
         if (precision == ZODI_FP32) return launch_kelsall<float>(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall<double>(m->k64, a, m->d_table64, m->d_nodes64, stream);
@@ -1041,7 +1048,7 @@ int zodi_peer_buffer_free(int device, void* ptr) {
 const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
     if (!m) return "";
     if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";
-    if (precision == ZODI_FP32 && !m->k32.scatter && !m->no_x2 && pick_lanes(n / 2, m->k32.n_nodes) == 1)
+    if (precision == ZODI_FP32 && !m->no_x2 && pick_lanes(n / 2, m->k32.n_nodes) == 1)
         return "zodi_los_kelsall_x2_kernel";
     return "zodi_los_kelsall_kernel";
 }

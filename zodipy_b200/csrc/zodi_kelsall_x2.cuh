@@ -44,6 +44,18 @@ ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v
 ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
 ZODI_HD F2 lg2_2(F2 v) { return f2(Math<float>::log2_(v.x), Math<float>::log2_(v.y)); }
 ZODI_HD F2 rsq_2(F2 v) { return f2(Math<float>::rsqrt_(v.x), Math<float>::rsqrt_(v.y)); }
+ZODI_HD F2 acos_neg2(F2 v) { return f2(Math<float>::acos_(-v.x), Math<float>::acos_(-v.y)); }
+ZODI_HD F2 clamp1_2(F2 v) {
+    return f2(fmaxf(-1.0f, fminf(1.0f, v.x)), fmaxf(-1.0f, fminf(1.0f, v.y)));
+}
+// Phi(Theta) / R_h^2 for both halves (node_source<float, true>'s scattering block).
+ZODI_HD F2 scatter_term2(const KelsallModel<float>& K, F2 ux, F2 uy, F2 uz, F2 xh, F2 yh, F2 zh, F2 rh_inv) {
+    const F2 ct = clamp1_2(mul2(fma2(ux, xh, fma2(uy, yh, mul2(uz, zh))), rh_inv));
+    const F2 th = acos_neg2(ct);
+    const F2 ph = f2(phase_function<float>(th.x, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_poly),
+                     phase_function<float>(th.y, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_poly));
+    return mul2(mul2(ph, rh_inv), rh_inv);
+}
 ZODI_HD F2 sqrt_2(F2 v) { return f2(Math<float>::sqrt_(v.x), Math<float>::sqrt_(v.y)); }
 
 // Table lookup for two temperatures (same arithmetic as table_at<float>).
@@ -90,18 +102,20 @@ ZODI_HD F2 band_radial2(F2 Rh2, float by) {
 
 // Adds w*B * n_band to acc, n_band = exp(-s^6) (1 + s^4/v) * (rinv * rad); skipped (n_band == 0)
 // when every lane of the warp is far enough from the band plane for exp(-s^6) to flush to zero.
-ZODI_HD void band_accumulate2(F2& acc, F2 wB, F2 xh, F2 yh, F2 zh, F2 rinv, F2 rinv_rad, float bx,
-                              float by, float bz, float c3) {
+template <bool SCATTER>
+ZODI_HD void band_accumulate2(F2& acc, F2& accS, F2 wB, F2 wF, F2 xh, F2 yh, F2 zh, F2 rinv, F2 rinv_rad,
+                              float bx, float by, float bz, float c3) {
     const F2 sz = mul2(fma2(xh, bx, fma2(yh, by, mul2(zh, bz))), rinv);
     const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2), s6 = mul2(s4, s2);
     if (warp_any(s6.x <= Math<float>::kEx2Underflow || s6.y <= Math<float>::kEx2Underflow)) {
         const F2 n = mul2(mul2(ex2_neg2(s6), fma2(s4, c3, 1.0f)), rinv_rad);
         acc = fma2(wB, n, acc);
+        if (SCATTER) accS = fma2(wF, n, accS);
     }
 }
 
 // Group A (cloud + band1..3, thermal only) for two lines of sight; emit(ci, value_a, value_b).
-template <bool SHARE13, typename Emit>
+template <bool SHARE13, bool SCATTER, typename Emit>
 ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>* tab,
                                 const Pair<float>* nodes, const LosGeometry<float>& Ga,
                                 const LosGeometry<float>& Gb, uint32_t outside_mask, Emit emit) {
@@ -112,6 +126,7 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     const F2 ux = f2(Ga.ux, Gb.ux), uy = f2(Ga.uy, Gb.uy), uz = f2(Ga.uz, Gb.uz);
     const F2 ox = f2(Ga.ox, Gb.ox), oy = f2(Ga.oy, Gb.oy), oz = f2(Ga.oz, Gb.oz);
     F2 a0 = f2(0.f), a1 = f2(0.f), a2 = f2(0.f), a3 = f2(0.f);
+    F2 s0 = f2(0.f), s1 = f2(0.f), s2 = f2(0.f), s3 = f2(0.f);  // scattering accumulators
     for (int k = 0; k < K.n_nodes; ++k) {
         const Pair<float> nw = nodes[k];
         // shared source quantities (node_source<float, false>)
@@ -127,9 +142,11 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 rad2 = band_radial2(Rh2, K.b_y[1]);
         const F2 rad3 = SHARE13 ? rad1 : band_radial2(Rh2, K.b_y[2]);
         const F2 wB = mul2(B, nw.b);
-        band_accumulate2(a1, wB, xh, yh, zh, rinv, mul2(rinv, rad1), K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
-        band_accumulate2(a2, wB, xh, yh, zh, rinv, mul2(rinv, rad2), K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
-        band_accumulate2(a3, wB, xh, yh, zh, rinv, mul2(rinv, rad3), K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        F2 wF = f2(0.f);
+        if (SCATTER) wF = mul2(scatter_term2(K, ux, uy, uz, xh, yh, zh, rinv), nw.b);  // rinv == 1/R_h (bands are Sun-centred)
+        band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad1), K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+        band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad2), K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+        band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad3), K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
         // cloud
         const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
         const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
@@ -140,10 +157,11 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
         const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
         a0 = fma2(wB, n0, a0);
+        if (SCATTER) s0 = fma2(wF, n0, s0);
     }
-    // scalar kernel: h * fma(aB, acc, aS * 0) == h * (aB * acc)
-    const F2 r0 = mul2(h, mul2(a0, K.aB[0])), r1 = mul2(h, mul2(a1, K.aB[1]));
-    const F2 r2 = mul2(h, mul2(a2, K.aB[2])), r3 = mul2(h, mul2(a3, K.aB[3]));
+    // scalar kernel: h * fma(aB, accB, aS * accS)   (accS == 0 without scattering)
+    const F2 r0 = mul2(h, fma2(a0, K.aB[0], mul2(s0, K.aS[0]))), r1 = mul2(h, fma2(a1, K.aB[1], mul2(s1, K.aS[1])));
+    const F2 r2 = mul2(h, fma2(a2, K.aB[2], mul2(s2, K.aS[2]))), r3 = mul2(h, fma2(a3, K.aB[3], mul2(s3, K.aS[3])));
     emit(0, r0.x, r0.y); emit(1, r1.x, r1.y); emit(2, r2.x, r2.y); emit(3, r3.x, r3.y);
 }
 
@@ -152,7 +170,7 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
 // the low half and the feature in the high half of every register pair; only the feature's
 // longitude term (atan2) is scalar.  Same operations as kelsall_ring<float,false> /
 // kelsall_feature<float,false> (bit-identical results).  emit(ring_value, feature_value).
-template <typename Emit>
+template <bool SCATTER, typename Emit>
 ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pair<float>* tab,
                                          const Pair<float>* nodes, const LosGeometry<float>& G,
                                          double dex, double dey, uint32_t outside_mask, Emit emit) {
@@ -164,7 +182,7 @@ ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pai
     const float cr = float(cos(th)), sr = float(sin(th));
     const F2 R0 = f2(-K.r_R, -K.f_R), c2 = f2(K.r_c2, K.f_c2), c3 = f2(K.r_c3, K.f_c3);
     const F2 nx = f2(K.rnx, K.fnx), ny = f2(K.rny, K.fny), nz = f2(K.rnz, K.fnz);
-    F2 acc = f2(0.f);
+    F2 acc = f2(0.f), accS = f2(0.f);
     for (int k = 0; k < K.n_nodes; ++k) {
         const Pair<float> nw = nodes[k];
         const F2 R_los = fma2(h, nw.a, mid);
@@ -177,9 +195,14 @@ ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pai
         const float xr = fmaf(xh.y, cr, yh.y * sr), yr = fmaf(yh.y, cr, -(xh.y * sr));
         const float dth = Math<float>::atan2_abs_(yr, xr);  // only dth^2 is used
         const F2 e = fma2(mul2(d, d), c2, fma2(f2(fabsf(Zc.x), fabsf(Zc.y)), c3, f2(0.f, dth * dth * K.f_c5)));
-        acc = fma2(mul2(B, nw.b), ex2_2(e), acc);
+        const F2 n = ex2_2(e);
+        acc = fma2(mul2(B, nw.b), n, acc);
+        if (SCATTER) {
+            const F2 F = scatter_term2(K, f2(G.ux), f2(G.uy), f2(G.uz), xh, yh, zh, rsq_2(Rh2));
+            accS = fma2(mul2(F, nw.b), n, accS);
+        }
     }
-    emit(hr * (K.aB[4] * acc.x), hf * (K.aB[5] * acc.y));
+    emit(hr * fmaf(K.aB[4], acc.x, K.aS[4] * accS.x), hf * fmaf(K.aB[5], acc.y, K.aS[5] * accS.y));
 }
 
 }  // namespace zodi

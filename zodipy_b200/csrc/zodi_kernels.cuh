@@ -217,7 +217,7 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
 // Packed-fp32 fused kernel: every thread integrates TWO lines of sight (j and j + 256 of its CTA's
 // 512) with FFMA2/FMUL2/FADD2 for the cloud + bands group (zodi_kelsall_x2.cuh); ring and feature
 // reuse the scalar routines.  fp32, thermal-only, large-N (L = 1) case = the benchmarked path.
-template <bool HAS_RF, bool SHARE13, int MIN_CTAS>
+template <bool HAS_RF, bool SHARE13, bool SCATTER, int MIN_CTAS>
 __global__ void __launch_bounds__(kThreads, MIN_CTAS)
 zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
                            const __grid_constant__ LaunchArgs args,
@@ -254,12 +254,12 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
             if (act1) store_out<float>(args, ci, j1, vb);
         }
     };
-    kelsall_group_a_x2<SHARE13>(model, s_table, s_nodes, G[0], G[1], args.outside_mask, emit2);
+    kelsall_group_a_x2<SHARE13, SCATTER>(model, s_table, s_nodes, G[0], G[1], args.outside_mask, emit2);
     if (HAS_RF) {
         float ring[2], feat[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
-            kelsall_ring_feature_packed(model, s_table, s_nodes, G[q], ex[q], ey[q], args.outside_mask,
+            kelsall_ring_feature_packed<SCATTER>(model, s_table, s_nodes, G[q], ex[q], ey[q], args.outside_mask,
                                         [&](float r, float f) { ring[q] = r; feat[q] = f; });
         emit2(4, ring[0], ring[1]);
         emit2(5, feat[0], feat[1]);
