@@ -177,10 +177,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-n", type=float, default=2.1e8)
     ap.add_argument("--skip-fp64-above", type=float, default=6e7)
+    ap.add_argument("--scatter-only", action="store_true", help="only the 1.25 um scattering case, nside 1024")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     earth = torch.as_tensor(EARTH, device=dev)
     Q = zp.Quantity
+    if args.scatter_only:
+        run("extra: dirbe 1.25um (scattering) nside=1024", zp.Model(Q(1.25, "um")), healpix_dirs(1024, dev), earth,
+            earth, args.skip_fp64_above)
+        return
 
     run("1: dirbe 25um nside=64", zp.Model(Q(25.0, "um")), healpix_dirs(64, dev), earth, earth, args.skip_fp64_above)
     x = np.linspace(9.0, 15.0, 10)

@@ -269,7 +269,8 @@ cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a,
                               const Pair<float>* nodes, cudaStream_t stream) {
     const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
     // cloud+bands only: 5 CTAs/SM (48 registers) measured 5 % faster than 4 CTAs/SM (60 registers)
-    // on B200; the ring/feature loops and the scattering terms need more registers (4 / 3 CTAs/SM).
+    // on B200; the ring/feature loops and the scattering terms need more registers (4 / 3 CTAs/SM; 4 CTAs/SM
+    // with scattering measured equal to 3).
     constexpr int kMinCtas = SCATTER ? 3 : (HAS_RF ? 4 : 5);
     zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, kMinCtas>
         <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);

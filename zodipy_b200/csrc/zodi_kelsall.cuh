@@ -37,7 +37,8 @@ struct KelsallModel {
     Real t_top;    // n_temps - 1
     Real mhd;      // -delta / 2
     Real C1p, C2p, C3l;   // phase function: C1, C2, C3*log2e
-    int phase_poly_ok;    // fp32: cancellation-free polynomial form (zodi_device.cuh: phase_function)
+    int phase_poly_ok;    // fp32: cancellation-free polynomial form (zodi_device.cuh: phase_of_cos)
+    int phase_terms;      // 8 or kPhaseTerms: coefficients that are not zero padding
     Real phase_poly[kPhaseTerms];
     Real aB[6];    // (1 - albedo_c) * emissivity_c * amplitude_c     (thermal)
     Real aS[6];    // albedo_c * F_sun * N_phase * amplitude_c        (scattering)
@@ -110,8 +111,7 @@ ZODI_HD NodeSource<Real> node_source(const KelsallModel<Real>& K, const Pair<Rea
         const Real rh_inv = M::rsqrt_(s.Rh2);
         Real ct = M::fma_(ux, s.xh, M::fma_(uy, s.yh, uz * s.zh)) * rh_inv;
         ct = M::max_(Real(-1), M::min_(Real(1), ct));
-        const Real th = M::acos_(-ct);
-        s.F = phase_function<Real>(th, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_poly) * rh_inv * rh_inv;
+        s.F = phase_of_cos<Real>(ct, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_terms, K.phase_poly) * rh_inv * rh_inv;
     }
     return s;
 }

@@ -44,19 +44,54 @@ ZODI_HD F2 ex2_2(F2 v) { return f2(Math<float>::exp2_(v.x), Math<float>::exp2_(v
 ZODI_HD F2 ex2_neg2(F2 v) { return f2(Math<float>::exp2_neg_(v.x), Math<float>::exp2_neg_(v.y)); }
 ZODI_HD F2 lg2_2(F2 v) { return f2(Math<float>::log2_(v.x), Math<float>::log2_(v.y)); }
 ZODI_HD F2 rsq_2(F2 v) { return f2(Math<float>::rsqrt_(v.x), Math<float>::rsqrt_(v.y)); }
-ZODI_HD F2 acos_neg2(F2 v) { return f2(Math<float>::acos_(-v.x), Math<float>::acos_(-v.y)); }
+ZODI_HD F2 sqrt_2(F2 v) { return f2(Math<float>::sqrt_(v.x), Math<float>::sqrt_(v.y)); }
 ZODI_HD F2 clamp1_2(F2 v) {
     return f2(fmaxf(-1.0f, fminf(1.0f, v.x)), fmaxf(-1.0f, fminf(1.0f, v.y)));
+}
+// asin_unit() for both halves: the polynomial runs packed, the selects per half.
+ZODI_HD F2 asin_unit2(F2 c) {
+    const F2 a = f2(fabsf(c.x), fabsf(c.y));
+    const bool bx = a.x > 0.5f, by = a.y > 0.5f;
+    const F2 zb = fma2(a, f2(-0.5f), f2(0.5f)), zs = mul2(a, a);
+    const F2 z = f2(bx ? zb.x : zs.x, by ? zb.y : zs.y);
+    const F2 s = f2(bx ? Math<float>::sqrt_(z.x) : a.x, by ? Math<float>::sqrt_(z.y) : a.y);
+    F2 p = fma2(f2(kAsinP4), z, f2(kAsinP3));
+    p = fma2(p, z, f2(kAsinP2));
+    p = fma2(p, z, f2(kAsinP1));
+    p = fma2(p, z, f2(kAsinP0));
+    p = fma2(mul2(s, z), p, s);
+    const F2 r = fma2(p, f2(-2.0f), f2(1.57079637f));
+    return f2(copysignf(bx ? r.x : p.x, c.x), copysignf(by ? r.y : p.y, c.y));
+}
+// phase_of_cos<float>() for both halves.
+ZODI_HD F2 phase_of_cos2(const KelsallModel<float>& K, F2 c) {
+    const F2 t = asin_unit2(c);
+    if (!K.phase_poly_ok) {
+        const F2 th = add2(t, 1.57079637f);
+        return f2(K.C1p + K.C2p * th.x + Math<float>::exp2_(K.C3l * th.x),
+                  K.C1p + K.C2p * th.y + Math<float>::exp2_(K.C3l * th.y));
+    }
+    F2 p;
+    if (K.phase_terms <= 8) {
+        p = f2(K.phase_poly[7]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 6; k >= 0; --k) p = fma2(p, t, f2(K.phase_poly[k]));
+    } else {
+        p = f2(K.phase_poly[kPhaseTerms - 1]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = kPhaseTerms - 2; k >= 0; --k) p = fma2(p, t, f2(K.phase_poly[k]));
+    }
+    return p;
 }
 // Phi(Theta) / R_h^2 for both halves (node_source<float, true>'s scattering block).
 ZODI_HD F2 scatter_term2(const KelsallModel<float>& K, F2 ux, F2 uy, F2 uz, F2 xh, F2 yh, F2 zh, F2 rh_inv) {
     const F2 ct = clamp1_2(mul2(fma2(ux, xh, fma2(uy, yh, mul2(uz, zh))), rh_inv));
-    const F2 th = acos_neg2(ct);
-    const F2 ph = f2(phase_function<float>(th.x, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_poly),
-                     phase_function<float>(th.y, K.C1p, K.C2p, K.C3l, K.phase_poly_ok, K.phase_poly));
-    return mul2(mul2(ph, rh_inv), rh_inv);
+    return mul2(mul2(phase_of_cos2(K, ct), rh_inv), rh_inv);
 }
-ZODI_HD F2 sqrt_2(F2 v) { return f2(Math<float>::sqrt_(v.x), Math<float>::sqrt_(v.y)); }
 
 // Table lookup for two temperatures (same arithmetic as table_at<float>).
 ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {

@@ -106,19 +106,25 @@ inline void derive_component(const zodi_model_desc& d, const zodi_component_desc
     }
 }
 
-// Taylor coefficients of C1 + C2 T + exp(C3 T) about T = pi/2 (see phase_function()); returns
-// whether kPhaseTerms terms reach 1e-9 relative to the leading exponential term.
-inline bool phase_polynomial(double C1, double C2, double C3, double* a) {
+// Taylor coefficients of C1 + C2 T + exp(C3 T) about T = pi/2 (see phase_of_cos()).  Returns the
+// number of terms kept (8 or kPhaseTerms, the rest zero-padded) such that the truncation error on
+// |T - pi/2| <= pi/2 is below 1e-9 of the leading exponential term, or 0 if kPhaseTerms do not
+// reach that (then the device evaluates the literal form).
+inline int phase_polynomial(double C1, double C2, double C3, double* a) {
     const double t0 = 0.5 * kPi, E = std::exp(C3 * t0);
     a[0] = C1 + C2 * t0 + E;
     a[1] = C2 + C3 * E;
     double term = C3 * E;
-    for (int k = 2; k < kPhaseTerms; ++k) {
-        term *= C3 / k;
-        a[k] = term;
+    int terms = 0;
+    for (int k = 2; k <= kPhaseTerms; ++k) {
+        term *= C3 / k;  // coefficient of t^k
+        // remainder after k terms <= |a_k| t0^k e^{|C3| t0}
+        if (!terms && (k == 8 || k == kPhaseTerms) &&
+            std::fabs(term) * std::pow(t0, k) * std::exp(std::fabs(C3) * t0) <= 1e-9 * E)
+            terms = k;
+        if (k < kPhaseTerms) a[k] = terms ? 0.0 : term;
     }
-    const double next = std::fabs(term * C3 / kPhaseTerms) * std::pow(t0, kPhaseTerms);
-    return next <= 1e-9 * E;
+    return terms;
 }
 
 template <typename To, typename From>
@@ -128,7 +134,7 @@ inline void narrow_model(const DevModel<From>& a, DevModel<To>& b) {
     b.has_feature = a.has_feature;
     b.t_min = (To)a.t_min; b.inv_dt = (To)a.inv_dt;
     b.C1 = (To)a.C1; b.C2 = (To)a.C2; b.C3 = (To)a.C3;
-    b.phase_poly_ok = a.phase_poly_ok;
+    b.phase_poly_ok = a.phase_poly_ok; b.phase_terms = a.phase_terms;
     for (int k = 0; k < kPhaseTerms; ++k) b.phase_poly[k] = (To)a.phase_poly[k];
     for (int i = 0; i < a.n_comps; ++i) {
         const DevComp<From>& s = a.comps[i];
@@ -150,7 +156,8 @@ inline void build_dev_model(const zodi_model_desc& d, DevModel<double>& M) {
     M.t_min = d.temps[0];
     M.inv_dt = (d.n_temps - 1) / (d.temps[d.n_temps - 1] - d.temps[0]);
     M.C1 = d.C1; M.C2 = d.C2; M.C3 = d.C3 * kLog2e;
-    M.phase_poly_ok = phase_polynomial(d.C1, d.C2, d.C3, M.phase_poly) ? 1 : 0;
+    M.phase_terms = phase_polynomial(d.C1, d.C2, d.C3, M.phase_poly);
+    M.phase_poly_ok = M.phase_terms ? 1 : 0;
     // _get_phase_normalization, scattering.py:53-59
     const double phase_norm =
         1.0 / (2.0 * kPi * (2.0 * d.C1 + kPi * d.C2 + (std::exp(d.C3 * kPi) + 1.0) / (d.C3 * d.C3 + 1.0)));
@@ -206,7 +213,8 @@ inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& 
     K.t_top = d.n_temps - 1;
     K.mhd = -0.5 * d.delta;
     K.C1p = d.C1; K.C2p = d.C2; K.C3l = d.C3 * kLog2e;
-    K.phase_poly_ok = phase_polynomial(d.C1, d.C2, d.C3, K.phase_poly) ? 1 : 0;
+    K.phase_terms = phase_polynomial(d.C1, d.C2, d.C3, K.phase_poly);
+    K.phase_poly_ok = K.phase_terms ? 1 : 0;
     const double phase_norm =
         1.0 / (2.0 * kPi * (2.0 * d.C1 + kPi * d.C2 + (std::exp(d.C3 * kPi) + 1.0) / (d.C3 * d.C3 + 1.0)));
     K.scatter = 0;
@@ -254,7 +262,7 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     b.scatter = a.scatter; b.share13 = a.share13;
 #define ZN(f) b.f = (To)a.f
     ZN(t_scale); ZN(t_ofs); ZN(t_top); ZN(mhd); ZN(C1p); ZN(C2p); ZN(C3l);
-    b.phase_poly_ok = a.phase_poly_ok;
+    b.phase_poly_ok = a.phase_poly_ok; b.phase_terms = a.phase_terms;
     for (int i = 0; i < kPhaseTerms; ++i) ZN(phase_poly[i]);
     for (int i = 0; i < 6; ++i) { ZN(aB[i]); ZN(aS[i]); }
     ZN(cx0); ZN(cy0); ZN(cz0); ZN(cnx); ZN(cny); ZN(cnz);
