@@ -82,7 +82,8 @@ def run(label, model, u, obs, earth, skip_fp64_above):
     # the oracle derives its early-out flags from the subset's observers; they equal the global
     # ones here because every synthetic observer stays inside all outer cutoffs
     ref = oracle.evaluate(model.spec, u_s, obs_s, earth_s).sum(axis=0)
-    res = {"config": label, "n_los": n, "ncomps": model.ncomps, "evaluations": units, "kernel": dm.kernel_name}
+    res = {"config": label, "n_los": n, "ncomps": model.ncomps, "evaluations": units,
+           "kernel": {p: dm.kernel_name_for(n, p) for p in ("fp32", "fp64")}}
     for precision, out_dtype, tol in (("fp32", np.float32, 1e-5), ("fp64", np.float64, 1e-10)):
         if precision == "fp64" and n > skip_fp64_above:
             continue

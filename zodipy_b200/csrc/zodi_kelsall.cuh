@@ -57,35 +57,14 @@ struct KelsallModel {
 };
 
 // --- table lookup -----------------------------------------------------------------------------
-// t = table coordinate (knot units).  fp32: floor via the 2^23 magic constant (stays on the FMA/ALU
-// pipes; FRND/F2I would compete with MUFU for the XU pipe).  round(t - 0.5) differs from floor(t)
-// only when t is an exact integer, where both neighbouring segments give the same value.
+// t = table coordinate (knot units); see table_coord() in zodi_device.cuh.
 template <typename Real>
-ZODI_HD Real table_at(const Pair<Real>* tab, Real t, Real t_top);
-
-template <>
-ZODI_HD float table_at<float>(const Pair<float>* tab, float t, float t_top) {
-    t = fminf(fmaxf(t, 0.0f), t_top);
-    const float magic = 12582912.0f;     // 1.5 * 2^23: (x + magic) rounds x to an integer
-    const float s = (t - 0.5f) + magic;  // integer-valued: round-half-even(t - 0.5) in [0, t_top]
-#if defined(__CUDA_ARCH__)
-    const int idx = __float_as_int(s) - 0x4B400000;
-#else
-    int bits;
-    memcpy(&bits, &s, 4);
-    const int idx = bits - 0x4B400000;
-#endif
-    // idx may equal t_top (last knot): its stored delta is 0, so B = B_last exactly.
-    const Pair<float> e = tab[idx];
-    return fmaf(e.b, t - (s - magic), e.a);
-}
-
-template <>
-ZODI_HD double table_at<double>(const Pair<double>* tab, double t, double t_top) {
-    t = fmin(fmax(t, 0.0), t_top);
-    const double fl = fmin(floor(t), t_top - 1.0);
-    const Pair<double> e = tab[(int)fl];
-    return fma(e.b, t - fl, e.a);
+ZODI_HD Real table_at(const Pair<Real>* tab, Real t, Real t_top) {
+    int idx;
+    Real frac;
+    table_coord<Real>(t, t_top, idx, frac);
+    const Pair<Real> e = tab[idx];  // idx may equal t_top (last knot): its stored delta is 0
+    return Math<Real>::fma_(e.b, frac, e.a);
 }
 
 // Shared per-node source quantities.

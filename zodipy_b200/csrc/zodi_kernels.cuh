@@ -145,6 +145,7 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
     Pair<Real>* s_nodes = s_table + model.n_temps;
     for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
     for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    if (sizeof(Real) == sizeof(double)) fp64_tables_stage();
     __syncthreads();
 
     constexpr int kLosPerCta = kThreads / L;
@@ -189,6 +190,7 @@ zodi_los_kelsall_kernel(const __grid_constant__ KelsallModel<Real> model,
     __shared__ Pair<Real> s_nodes[kFastMaxNodes];
     for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
     for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    if (sizeof(Real) == sizeof(double)) fp64_tables_stage();
     __syncthreads();
 
     constexpr int kLosPerCta = kThreads / L;
@@ -286,6 +288,7 @@ zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
         s_tables[i] = (i < model.n_bands * nt) ? g_tables[i] : zero;  // padded bands: zero source
     }
     for (int i = threadIdx.x; i < model.base.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    if (sizeof(Real) == sizeof(double)) fp64_tables_stage();
     __syncthreads();
 
     const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -315,6 +318,8 @@ __global__ void zodi_healpix_vectors_kernel(const __grid_constant__ LaunchArgs a
 __global__ void zodi_number_density_kernel(const __grid_constant__ DevModel<double> model,
                                            const double* __restrict__ xyz, int64_t n, int64_t stride,
                                            double ex, double ey, double* __restrict__ out, int64_t out_stride) {
+    fp64_tables_stage();
+    __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const double x = xyz[j], y = xyz[stride + j], z = xyz[2 * stride + j];

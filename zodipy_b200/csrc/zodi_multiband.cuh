@@ -30,31 +30,10 @@ struct MultiBandModel {
     Real C1p[kMaxBands], C2p[kMaxBands], C3l[kMaxBands];  // phase function per band (C3 * log2e)
 };
 
-// Table coordinate -> (segment index, fraction); same arithmetic as table_at<Real>().
+// Table coordinate -> (segment index, fraction): table_coord() of zodi_device.cuh.
 template <typename Real>
-ZODI_HD void table_locate(Real t, Real t_top, int& idx, Real& frac);
-
-template <>
-ZODI_HD void table_locate<float>(float t, float t_top, int& idx, float& frac) {
-    t = fminf(fmaxf(t, 0.0f), t_top);
-    const float magic = 12582912.0f;
-    const float s = (t - 0.5f) + magic;
-#if defined(__CUDA_ARCH__)
-    idx = __float_as_int(s) - 0x4B400000;
-#else
-    int bits;
-    memcpy(&bits, &s, 4);
-    idx = bits - 0x4B400000;
-#endif
-    frac = t - (s - magic);
-}
-
-template <>
-ZODI_HD void table_locate<double>(double t, double t_top, int& idx, double& frac) {
-    t = fmin(fmax(t, 0.0), t_top);
-    const double fl = fmin(floor(t), t_top - 1.0);
-    idx = (int)fl;
-    frac = t - fl;
+ZODI_HD void table_locate(Real t, Real t_top, int& idx, Real& frac) {
+    table_coord<Real>(t, t_top, idx, frac);
 }
 
 // Per-node quantities shared by all bands.
