@@ -176,6 +176,9 @@ zodi_los_generic_kernel(const __grid_constant__ DevModel<Real> model,
 // Static shared capacity of the fused kernel (the reference uses 100 knots and 50 nodes); larger
 // tables / rules take the generic kernel, whose staging area is sized dynamically.
 constexpr int kFastMaxTemps = 128;
+// multi-band kernels keep one table per band in (static, <= 48 KB) shared memory next to the 16 KB of
+// fp64 log2 / exp2 tables: 16 bands x 104 knots x 16 B = 26 KB.  The reference's table has 100 knots.
+constexpr int kMultiBandMaxTemps = 104;
 constexpr int kFastMaxNodes = 128;
 
 template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, int L>
@@ -280,7 +283,7 @@ zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
                           const __grid_constant__ LaunchArgs args,
                           const Pair<Real>* __restrict__ g_tables,   // [n_bands][n_temps]
                           const Pair<Real>* __restrict__ g_nodes) {
-    __shared__ Pair<Real> s_tables[NB * kFastMaxTemps];
+    __shared__ Pair<Real> s_tables[NB * kMultiBandMaxTemps];
     __shared__ Pair<Real> s_nodes[kFastMaxNodes];
     const int nt = model.base.n_temps;
     for (int i = threadIdx.x; i < NB * nt; i += blockDim.x) {
