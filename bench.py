@@ -40,6 +40,14 @@ SFU_PER_UNIT = 7.0
 EXEC_ISSUE_PER_UNIT = 155.4 / 8   # warp-instruction issue slots
 EXEC_MUFU_PER_UNIT = 20.6 / 8     # XU-pipe instructions
 EXEC_FMA_CYCLES_PER_UNIT = 2 * 80.5 / 8  # FMA-pipe cycles (packed FFMA2/FMUL2/FADD2 take 2)
+# Same for the fp64 kernel, profiles/r1_ncu_fp64_planck18_nside1024.md: 80.3 thread-instructions per
+# evaluation of which 43.5 % go to the FP64 pipe (one warp instruction per two issue cycles).
+EXEC64_ISSUE_PER_UNIT = 80.3
+EXEC64_FP64_PER_UNIT = 80.3 * 0.435
+# DRAM traffic per line of sight of the fp32 kernel with array inputs, `ncu --set full`
+# (profiles/r1_ncu_kelsall_x2_fp32_nside1024.md: 302.07 MB read + 41.39 MB written / 12 582 912):
+# the algorithmic 24 B in + 4 B out less the output lines still in L2 when the kernel ends.
+TRAFFIC_BYTES_PER_LOS_FP32 = (302.065408e6 + 41.389056e6) / 12582912
 EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])  # 2022-01-14, SURVEY.md 8(d)
 
 
@@ -411,7 +419,11 @@ def run_b200(args):
     achieved = kernel_units_per_s * FLOPS_PER_UNIT
     roofline = {
         "bound": precision, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak,
+        "traffic": TRAFFIC_BYTES_PER_LOS_FP32 * n_local if precision == "fp32" else None,
+        "traffic_from": ("profiles/r1_ncu_kelsall_x2_fp32_nside1024.md: dram__bytes_read + write of one launch at "
+                         "nside 1024 = 27.3 B per line of sight, scaled to this launch's lines of sight")
+                        if precision == "fp32" else None,
         "kernel": dm.kernel_name_for(n_local, precision), "kernel_ms": kernel_ms,
         "flops_per_unit_canonical": FLOPS_PER_UNIT, "sfu_per_unit_canonical": SFU_PER_UNIT,
         "sfu_frac": kernel_units_per_s * SFU_PER_UNIT / peak_mufu,
@@ -419,7 +431,11 @@ def run_b200(args):
                            "mufu_tops": peak_mufu / 1e12,
                            "how": "zodi_peak_probe: FFMA / DFMA / MUFU.EX2 microbenchmarks, best of 5, "
                                   "same process, same GPU"},
-        "executed": None if (precision != "fp32" or "x2" not in dm.kernel_name_for(n_local, precision)) else {
+        "executed": {
+            "issue_slot_util": kernel_units_per_s * EXEC64_ISSUE_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+            "fp64_pipe_util": kernel_units_per_s * 2 * EXEC64_FP64_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+            "counts_from": "profiles/r1_ncu_fp64_planck18_nside1024.md"}
+        if precision == "fp64" else None if "x2" not in dm.kernel_name_for(n_local, precision) else {
             # pipe utilisation implied by the measured rate and the executed counts of the ncu capture
             "issue_slot_util": kernel_units_per_s * EXEC_ISSUE_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
             "xu_pipe_util": kernel_units_per_s * EXEC_MUFU_PER_UNIT / peak_mufu,
@@ -457,6 +473,10 @@ def run_b200(args):
         ups64 = per_gpu_units / (ms64 * 1e-3)
         fp64 = {"kernel_ms": ms64, "evals_per_s_per_gpu": ups64,
                 "roofline_frac_fp64_canonical": ups64 * FLOPS_PER_UNIT / peak_fp64,
+                "executed": {
+                    "issue_slot_util": ups64 * EXEC64_ISSUE_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+                    "fp64_pipe_util": ups64 * 2 * EXEC64_FP64_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
+                    "counts_from": "profiles/r1_ncu_fp64_planck18_nside1024.md"},
                 "max_rel_err_vs_oracle": float(np.max(np.abs(got64 - ref) / np.abs(ref))),
                 "tolerance": 1e-10}
 
