@@ -160,3 +160,34 @@ extern "C" int zodi_emu_spline(int n, const double* x, const double* y, double* 
     }
     return 0;
 }
+
+// Element-wise access to the device math for unit tests: op 0 = Math<double>::log2_, 1 = exp2_,
+// 2 = asin_unit (fp32), 3 = table_coord<double> fraction, 4 = table_coord<double> index.
+extern "C" int zodi_emu_math(int op, int64_t n, const double* x, double aux, double* y) {
+    for (int64_t i = 0; i < n; ++i) {
+        switch (op) {
+            case 0: y[i] = Math<double>::log2_(x[i]); break;
+            case 1: y[i] = Math<double>::exp2_(x[i]); break;
+            case 2: y[i] = (double)asin_unit((float)x[i]); break;
+            case 3: case 4: {
+                int idx; double frac;
+                table_coord<double>(x[i], aux, idx, frac);
+                y[i] = op == 3 ? frac : (double)idx;
+                break;
+            }
+            default: return 1;
+        }
+    }
+    return 0;
+}
+
+// phase_of_cos<float> with the polynomial the host builds for (C1, C2, C3); returns terms kept.
+extern "C" int zodi_emu_phase(double C1, double C2, double C3, int64_t n, const double* c, double* y) {
+    double poly64[kPhaseTerms];
+    float poly[kPhaseTerms];
+    const int terms = phase_polynomial(C1, C2, C3, poly64);
+    for (int k = 0; k < kPhaseTerms; ++k) poly[k] = (float)poly64[k];
+    for (int64_t i = 0; i < n; ++i)
+        y[i] = (double)phase_of_cos<float>((float)c[i], (float)C1, (float)C2, (float)(C3 * kLog2e), terms ? 1 : 0, terms, poly);
+    return terms;
+}

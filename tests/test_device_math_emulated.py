@@ -128,3 +128,80 @@ def test_spline_builder_matches_scipy(emu, n):
         ref = CubicSpline(x, y).c
         scale = np.abs(ref).max(axis=1, keepdims=True)
         assert np.max(np.abs(c - ref) / scale) < 1e-11
+
+
+def _math(emu, op, x, aux=0.0):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert emu.zodi_emu_math(C.c_int(op), C.c_int64(x.size), ptr(x), C.c_double(aux), ptr(y)) == 0
+    return y
+
+
+def test_fp64_log2_table_routine(emu):
+    """Math<double>::log2_ (512-bin table + degree-3 polynomial): ~2 ulp over 120 octaves."""
+    rng = np.random.default_rng(5)
+    x = np.exp2(rng.uniform(-60, 60, 200_000))
+    err = np.abs(_math(emu, 0, x) - np.log2(x).astype(np.longdouble).astype(np.float64))
+    assert err.max() <= 4e-16 * np.maximum(1.0, np.abs(np.log2(x))).max()
+    near_one = 1.0 + rng.uniform(-1e-3, 1e-3, 100_000)  # |log2| small: absolute error matters
+    assert np.abs(_math(emu, 0, near_one) - np.log2(near_one)).max() <= 3e-16
+    special = _math(emu, 0, np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1.0, 2.0, 0.5]))
+    assert special[0] == -np.inf and np.isnan(special[1]) and special[2] == np.inf and np.isnan(special[3])
+    assert special[4] == -1074.0  # denormal: library path
+    np.testing.assert_allclose(special[5:], [0.0, 1.0, -1.0], rtol=0, atol=2.5e-16)  # table path, not exact
+
+
+def test_fp64_exp2_table_routine(emu):
+    """Math<double>::exp2_ (1024-bin table + degree-2 polynomial): <= 5e-16 relative on (-1020, 1020),
+    exact zero below, NaN propagated, exact powers of two exact."""
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-1019.9, 1019.9, 200_000), rng.uniform(-3, 3, 200_000)])
+    got, ref = _math(emu, 1, x), np.exp2(x)
+    assert (np.abs(got - ref) / ref).max() <= 5e-16
+    k = np.arange(-1019, 1020, dtype=np.float64)
+    np.testing.assert_array_equal(_math(emu, 1, k), np.exp2(k))
+    low = _math(emu, 1, np.array([-1020.0, -1020.5, -1075.0, -1e9, -1e300, -np.inf]))
+    np.testing.assert_array_equal(low, 0.0)
+    assert np.isnan(_math(emu, 1, np.array([np.nan, -np.nan]))).all()
+
+
+def test_fp64_table_coordinate_clamps(emu):
+    """table_coord<double>: np.interp's clamping expressed on the integer index."""
+    top = 99.0
+    t = np.array([-5.0, -1e-9, 0.0, 0.25, 41.75, 98.999, 99.0, 99.5, 1e12, np.inf])
+    idx, frac = _math(emu, 4, t, top), _math(emu, 3, t, top)
+    np.testing.assert_array_equal(idx, [0, 0, 0, 0, 41, 98, 99, 99, 99, 99])
+    np.testing.assert_allclose(frac[:6], [0.0, 0.0, 0.0, 0.25, 0.75, 0.999], rtol=0, atol=1e-12)
+    assert np.isnan(_math(emu, 3, np.array([np.nan]), top)[0])  # NaN temperature stays NaN
+
+
+def test_fp32_asin_routine(emu):
+    c = np.concatenate([np.linspace(-1, 1, 200_001), [1e-30, -1e-30, 0.5, -0.5, 0.50000006, 0.0]])
+    got = _math(emu, 2, c)
+    ref = np.arcsin(c.astype(np.float32).astype(np.float64))
+    assert np.abs(got - ref).max() <= 2.5e-7  # ~2 ulp of pi/2
+    small = np.abs(c) < 0.5
+    assert (np.abs(got[small] - ref[small]) <= 1.3e-7 * np.abs(ref[small]) + 1e-45).all()  # relative near 0
+
+
+@pytest.mark.parametrize("coeffs", [(-0.942, 0.121, -0.165), (-0.527, 0.187, -0.598), (-0.431, 0.172, -0.633),
+                                    (0.3, 0.05, -3.0)])
+def test_fp32_phase_function_polynomial(emu, coeffs):
+    """phase_of_cos<float>: C1 + C2 Theta + exp(C3 Theta) at Theta = arccos(-c) without cancellation.
+    The first three coefficient sets are DIRBE 1.25 / 2.2 / 3.5 um (source_params.py), the last one
+    forces the literal fallback (|C3| too large for 14 Taylor terms)."""
+    C1, C2, C3 = coeffs
+    c = np.linspace(-1, 1, 20_001)
+    y = np.empty_like(c)
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    terms = emu.zodi_emu_phase(C.c_double(C1), C.c_double(C2), C.c_double(C3), C.c_int64(c.size), ptr(c), ptr(y))
+    theta = np.arccos(-c.astype(np.float32).astype(np.float64))
+    ref = C1 + C2 * theta + np.exp(C3 * theta)
+    scale = np.abs(C1) + np.abs(C2) * np.pi + 1.0
+    if abs(C3) < 1.0:
+        assert terms in (8, 14)
+        assert (np.abs(y - ref) / np.abs(ref)).max() <= 2e-6  # relative to the (cancelled) value itself
+    else:
+        assert terms == 0
+        assert (np.abs(y - ref) / scale).max() <= 1e-6  # literal form: relative to the terms' size
