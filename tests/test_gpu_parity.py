@@ -258,7 +258,8 @@ def test_evaluate_healpix_equals_array_seam(precision):
 
 
 @pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um"),
-                                         ("planck13", 545.0, "GHz")])
+                                         ("planck13", 545.0, "GHz"), ("dirbe", 1.25, "um"),
+                                         ("dirbe", 3.5, "um")])  # the last two: scattering
 def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
     """The packed-fp32 kernel (FFMA2, two lines of sight per thread) performs the same operations
     as the scalar fused kernel: results must be bit-identical (incl. ragged tails, per-sample
