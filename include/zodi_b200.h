@@ -158,7 +158,10 @@ typedef struct {
     int32_t cyclic_rank;
     /* On-device ephemeris: when `ephemeris` is non-NULL, obs / earth (and their n_*, strides) are
      * ignored and sample j uses the spline positions at obstime[j] (obstime: n doubles, same
-     * memory kind as u).  outside_flags must then be supplied (see zodi_ephemeris_stats). */
+     * memory kind as u).  outside_flags must then be supplied (see zodi_ephemeris_stats).
+     * ZODI_MEM_HOST only: obstime may be NULL when the preceding zodi_ephemeris_stats call was given
+     * the same n host times - the copy it staged on the device is integrated from, so the times
+     * cross the bus once (32 instead of 40 B per sample in total). */
     zodi_ephemeris_t ephemeris;
     const double* obstime;
 } zodi_eval_args;
@@ -217,6 +220,10 @@ int zodi_ephemeris_positions(zodi_ephemeris_t eph, const double* t, int64_t n, i
  * max |observer|^2 (the global early-out flags, line_of_sight.py:72-73).  stats = 3 doubles (host). */
 int zodi_ephemeris_stats(zodi_ephemeris_t eph, const double* t, int64_t n, int32_t memory, void* stream,
                          double* stats);
+/* With ZODI_MEM_HOST, zodi_ephemeris_stats keeps its device copy of the n times in the handle (8 B
+ * per sample; the buffer is reused by later calls) for a following zodi_evaluate(obstime = NULL);
+ * this frees it (destroy does too). */
+int zodi_ephemeris_release_times(zodi_ephemeris_t eph);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 int zodi_evaluate(zodi_model_t model, const zodi_eval_args* args);

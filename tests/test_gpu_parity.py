@@ -358,6 +358,42 @@ def test_evaluate_tod_on_device_equals_host_interpolation(observer, precision):
     assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
 
 
+def test_staged_obstime_protocol():
+    """zodi_ephemeris_stats(host times) stages them on the device; zodi_evaluate(obstime=NULL) uses
+    that copy (same result as passing the times again) and refuses when nothing matching is staged."""
+    import ctypes as C
+
+    from zodipy_b200 import _cabi
+    from zodipy_b200.spec import outside_flags
+
+    n = 3 * (1 << 20) + 17  # several pipeline chunks
+    t0, dt, earth_knots, tk, t, u = _tod_inputs(n, seed=9)
+    model = zp.Model(zp.Quantity(25.0, "um"), precision="fp32")
+    dm, eph = model.device_model, engine.DeviceEphemeris(t0, dt, earth_knots)
+    r_max = eph.prepare(t, "earth")
+    flags = outside_flags(model.spec, r_max)
+
+    def call(obstime_ptr, count):
+        out = np.empty(count, dtype=np.float32)
+        a = _cabi.EvalArgs()
+        a.n, a.u, a.u_stride = count, u.ctypes.data, n
+        a.outside_flags = flags.ctypes.data_as(_cabi.c_uint8_p)
+        a.precision, a.out_dtype, a.memory = 1, _cabi.OUT_F32, _cabi.MEM_HOST
+        a.out, a.out_stride = out.ctypes.data, count
+        a.ephemeris, a.obstime = eph._handle, obstime_ptr
+        return dm._lib.zodi_evaluate(dm._handle, C.byref(a)), out
+
+    rc, explicit = call(t.ctypes.data, n)
+    assert rc == 0
+    rc, staged = call(None, n)
+    assert rc == 0
+    np.testing.assert_array_equal(staged, explicit)
+    assert call(None, n - 1)[0] != 0  # staged copy is for n samples
+    eph.release_times()
+    assert call(None, n)[0] != 0
+    assert b"staged" in dm._lib.zodi_last_error()
+
+
 @pytest.mark.parametrize("name", ["dirbe", "planck18", "rrm-experimental"])
 def test_grid_number_density_matches_reference_functions(name):
     """grid_number_density (reference tests/test_model.py:94-123: shape; here also values against

@@ -102,6 +102,9 @@ struct zodi_ephemeris_s {
     double* d_earth = nullptr;
     double* d_obs = nullptr;      // NULL: observer = obs_scale * Earth
     double* d_stats = nullptr;    // 3 doubles: sum, max bits x2
+    double* d_times = nullptr;    // sample times staged by the last host-memory zodi_ephemeris_stats
+    int64_t n_times = 0;          // staged samples (0: nothing valid)
+    int64_t cap_times = 0;        // allocated samples (the buffer is reused across calls)
 };
 
 namespace {
@@ -392,7 +395,9 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
             return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
     }
     if (a->ephemeris) {
-        if (!a->obstime) return fail(ZODI_ERR_INVALID, "obstime must be non-NULL with an ephemeris");
+        if (!a->obstime && (a->memory != ZODI_MEM_HOST || !a->ephemeris->d_times || a->ephemeris->n_times != a->n))
+            return fail(ZODI_ERR_INVALID, "obstime is NULL and the ephemeris holds no staged times for n=%lld samples "
+                                          "(zodi_ephemeris_stats with host memory stages them)", (long long)a->n);
         if (!a->outside_flags)
             return fail(ZODI_ERR_INVALID, "outside_flags must be supplied with an ephemeris (zodi_ephemeris_stats)");
         if (a->ephemeris->device != m->device) return fail(ZODI_ERR_INVALID, "ephemeris lives on another device");
@@ -487,7 +492,10 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         if (!hp)
             CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
                                        (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
-        if (a->ephemeris)  // obstime only (8 B per sample instead of 48 B of positions)
+        const double* d_time = d_obs;
+        if (a->ephemeris && !a->obstime)  // times already on the device (staged by zodi_ephemeris_stats)
+            d_time = a->ephemeris->d_times + done;
+        else if (a->ephemeris)  // obstime only (8 B per sample instead of 48 B of positions)
             CU_CHECK(cudaMemcpyAsync(d_obs, a->obstime + done, (size_t)cn * sizeof(double),
                                      cudaMemcpyHostToDevice, s.stream));
         else
@@ -511,7 +519,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         la.out = s.d_out; la.out_stride = m->ws_chunk;
         la.n_peers = 0; la.peer_offset = 0; la.peer_stride = 0;
         set_healpix(la, hp, done);
-        if (a->ephemeris) set_ephemeris(la, a->ephemeris, d_obs);
+        if (a->ephemeris) set_ephemeris(la, a->ephemeris, d_time);
         if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
         CU_CHECK(launch_eval(m, la, a->precision, s.stream));
         CU_CHECK(cudaEventRecord(s.k1, s.stream));
@@ -722,9 +730,19 @@ int zodi_ephemeris_destroy(zodi_ephemeris_t e) {
     if (!e) return ZODI_OK;
     {
         DeviceGuard guard(e->device);
-        cudaFree(e->d_earth); cudaFree(e->d_obs); cudaFree(e->d_stats);
+        cudaFree(e->d_earth); cudaFree(e->d_obs); cudaFree(e->d_stats); cudaFree(e->d_times);
     }
     delete e;
+    return ZODI_OK;
+}
+
+int zodi_ephemeris_release_times(zodi_ephemeris_t e) {
+    if (!e) return ZODI_OK;
+    DeviceGuard guard(e->device);
+    cudaFree(e->d_times);
+    e->d_times = nullptr;
+    e->n_times = 0;
+    e->cap_times = 0;
     return ZODI_OK;
 }
 
@@ -786,9 +804,21 @@ int zodi_ephemeris_stats(zodi_ephemeris_t e, const double* t, int64_t n, int32_t
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", e->device);
     cudaStream_t st = memory == ZODI_MEM_DEVICE ? (cudaStream_t)stream : nullptr;
-    double* d_t; bool owned;
-    int rc = stage_times(t, n, memory, st, &d_t, &owned);
-    if (rc) return rc;
+    const double* d_t = t;
+    if (memory == ZODI_MEM_HOST) {
+        // keep the device copy: a following zodi_evaluate with obstime = NULL integrates from it
+        // instead of uploading the times a second time
+        e->n_times = 0;
+        if (e->cap_times < n) {
+            cudaFree(e->d_times);
+            e->d_times = nullptr; e->cap_times = 0;
+            CU_CHECK(cudaMalloc((void**)&e->d_times, (size_t)n * sizeof(double)));
+            e->cap_times = n;
+        }
+        e->n_times = n;
+        CU_CHECK(cudaMemcpyAsync(e->d_times, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        d_t = e->d_times;
+    }
     CU_CHECK(cudaMemsetAsync(e->d_stats, 0, 3 * sizeof(double), st));
     LaunchArgs la;
     std::memset(&la, 0, sizeof(la));
@@ -800,7 +830,6 @@ int zodi_ephemeris_stats(zodi_ephemeris_t e, const double* t, int64_t n, int32_t
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaMemcpyAsync(stats, e->d_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
-    if (owned) cudaFree(d_t);
     if (!e->d_obs) stats[2] = e->obs_scale * e->obs_scale * stats[1];  // observer = scale * Earth
     return ZODI_OK;
 }

@@ -10,6 +10,7 @@ device memory and streams; the compute is the library's CUDA kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -122,6 +123,11 @@ class DeviceEphemeris:
         out = (C.c_double * 3)()
         _cabi.check(self._lib.zodi_ephemeris_stats(self._handle, ptr, n, mem, stream, out))
         return out[0], float(np.sqrt(out[1])), float(np.sqrt(out[2]))
+
+    def release_times(self) -> None:
+        """Free the device copy of the sample times that ``stats`` keeps for host arrays (8 B per
+        sample, reused by later calls; freed with the ephemeris otherwise)."""
+        _cabi.check(self._lib.zodi_ephemeris_release_times(self._handle))
 
     def prepare(self, t, observer: str = "earth"):
         """Set the observer rule for the samples at times ``t`` and return the largest observer
@@ -347,7 +353,10 @@ class DeviceModel:
         args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
         args.out, args.out_stride = out_ptr, n
         args.stream = stream
-        args.ephemeris, args.obstime = ephemeris._handle, t_ptr
+        # host arrays: prepare() -> zodi_ephemeris_stats staged the times on the device; obstime = NULL
+        # integrates from that copy, so they cross the bus once
+        staged = not device_mem and not os.environ.get("ZODI_TOD_EXPLICIT_OBSTIME")  # env: A/B measurement only
+        args.ephemeris, args.obstime = ephemeris._handle, (None if staged else t_ptr)
         _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
         return out
 
