@@ -113,7 +113,7 @@ ZODI_HD void band_accumulate(Real& accB, Real& accS, Real wB, Real wF, Real xh, 
 }
 
 // 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20).
-// Beyond kRadialOne (R > ~1.25 delta_r: most of a line of sight that runs out to 5.2 AU) the term is
+// Beyond kRadialOne (R > ~1.2 delta_r: most of a line of sight that runs out to 5.2 AU) the term is
 // exactly 1; when the whole warp is there the power chain and the exponential are skipped.
 template <typename Real>
 ZODI_HD Real band_radial(Real Rh2, Real by) {

@@ -115,16 +115,16 @@ ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
 // MUFU pair is skipped when no lane of the warp is in the window where it matters.
 ZODI_HD F2 one_minus_exp2_neg2(F2 y) {
     const F2 small = mul2(y, fma2(y, fma2(y, 0.05550411f, -0.24022651f), 0.69314718f));
-    F2 direct = f2(1.0f);  // y > 126: 1 - 0
-    const bool need = (y.x >= 0.04508422f && y.x <= Math<float>::kEx2Underflow) ||
-                      (y.y >= 0.04508422f && y.y <= Math<float>::kEx2Underflow);
+    F2 direct = f2(1.0f);  // y > 25.05: 1 - 2^-y rounds to exactly 1 (2^-y < 2^-25)
+    const bool need = (y.x >= 0.04508422f && y.x <= 25.05f) || (y.y >= 0.04508422f && y.y <= 25.05f);
     if (warp_any(need)) direct = fma2(ex2_neg2(y), -1.0f, 1.0f);  // 1 - e
     return f2(y.x < 0.04508422f ? small.x : direct.x, y.y < 0.04508422f ? small.y : direct.y);
 }
 
-// y = R^2 log2e^(1/10) / delta_r^2, so y^10 = log2e (R/delta_r)^20.  Beyond y = 1.6225 (R > 1.25 delta_r,
-// most of a line of sight that runs out to 5.2 AU) y^10 > 126 and the term is exactly 1: when the whole
-// warp is there the power chain, the polynomial and the MUFU pair are skipped.
+// y = R^2 log2e^(1/10) / delta_r^2, so y^10 = log2e (R/delta_r)^20.  Beyond y = kRadialOne = 1.38
+// (R > 1.15 delta_r, most of a line of sight that runs out to 5.2 AU) 2^(-y^10) < 2^-25 and the term
+// rounds to exactly 1: when the whole warp is there the power chain, the polynomial and the MUFU pair
+// are skipped.
 ZODI_HD F2 band_radial2(F2 Rh2, float by) {
     const F2 y = mul2(Rh2, by);
     F2 rad = f2(1.0f);
