@@ -288,6 +288,22 @@ typedef enum {
     ZODI_PEAK_HBM_COPY = 3  /* device copy: bytes/s (read+write) */
 } zodi_peak_kind;
 int zodi_peak_probe(int device, int32_t kind, double* per_second);
+/* Element-wise evaluation of the device math routines the integrators are built from, ON the
+ * GPU (for tests: the host cannot reproduce MUFU seeds / shared-memory tables).  x, y: n doubles in
+ * host memory; single-precision routines convert x (and aux) to float first.  aux: second argument
+ * of the two-argument routines (atan2_abs(y = x[i], x = aux)). */
+typedef enum {
+    ZODI_MATH_LOG2_F64 = 0,
+    ZODI_MATH_EXP2_F64 = 1,
+    ZODI_MATH_RSQRT_F64 = 2,
+    ZODI_MATH_ATAN2_ABS_F64 = 3,
+    ZODI_MATH_ASIN_F32 = 4,
+    ZODI_MATH_ATAN2_ABS_F32 = 5,
+    ZODI_MATH_ONE_MINUS_EXP2_NEG_F32 = 6,
+    ZODI_MATH_EXP2_F32 = 7,
+    ZODI_MATH_LOG2_F32 = 8
+} zodi_math_op;
+int zodi_device_math(int device, int32_t op, int64_t n, const double* x, double aux, double* y);
 /* Number of kernels this library launched on behalf of the calling process (all threads). */
 int64_t zodi_kernel_launch_count(void);
 /* Device time [ms] of the LAST zodi_evaluate kernel(s) issued with ZODI_MEM_HOST memory

@@ -162,7 +162,8 @@ extern "C" int zodi_emu_spline(int n, const double* x, const double* y, double* 
 }
 
 // Element-wise access to the device math for unit tests: op 0 = Math<double>::log2_, 1 = exp2_,
-// 2 = asin_unit (fp32), 3 = table_coord<double> fraction, 4 = table_coord<double> index.
+// 2 = asin_unit (fp32), 3 = table_coord<double> fraction, 4 = table_coord<double> index,
+// 5 = Math<double>::atan2_abs_(x[i], aux).
 extern "C" int zodi_emu_math(int op, int64_t n, const double* x, double aux, double* y) {
     for (int64_t i = 0; i < n; ++i) {
         switch (op) {
@@ -175,6 +176,7 @@ extern "C" int zodi_emu_math(int op, int64_t n, const double* x, double aux, dou
                 y[i] = op == 3 ? frac : (double)idx;
                 break;
             }
+            case 5: y[i] = Math<double>::atan2_abs_(x[i], aux); break;
             default: return 1;
         }
     }

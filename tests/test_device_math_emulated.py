@@ -176,6 +176,21 @@ def test_fp64_table_coordinate_clamps(emu):
     assert np.isnan(_math(emu, 3, np.array([np.nan]), top)[0])  # NaN temperature stays NaN
 
 
+def test_fp64_atan2_abs_routine(emu):
+    """Math<double>::atan2_abs_ (65-entry table + series): |atan2(y, x)| to ~2 ulp of pi, all octants."""
+    rng = np.random.default_rng(8)
+    for x in (1.0, -1.0, 0.37, -2.5, 1e-3, -1e-3, 0.0):
+        y = np.concatenate([rng.uniform(-3, 3, 50_000), rng.uniform(-1e-3, 1e-3, 10_000),
+                            [0.0, x, -x, 1e-300, 5.0]])
+        got = _math(emu, 5, y, aux=x)
+        ref = np.abs(np.arctan2(y, x))
+        assert np.abs(got - ref).max() <= 9e-16, x
+        small = np.abs(y) < 1e-2 * abs(x)
+        if x > 0 and small.any():  # near the axis the angle itself is small: relative accuracy
+            assert (np.abs(got[small] - ref[small]) <= 4e-16 * ref[small] + 1e-300).all()
+    assert _math(emu, 5, np.array([0.0]), aux=0.0)[0] == 0.0
+
+
 def test_fp32_asin_routine(emu):
     c = np.concatenate([np.linspace(-1, 1, 200_001), [1e-30, -1e-30, 0.5, -0.5, 0.50000006, 0.0]])
     got = _math(emu, 2, c)

@@ -358,6 +358,46 @@ def test_evaluate_tod_on_device_equals_host_interpolation(observer, precision):
     assert max_rel_total(got[:, sel], ref_o) <= TOL[precision][0]
 
 
+def test_device_math_routines_on_gpu():
+    """The transcendental routines of csrc/zodi_device.cuh evaluated on the GPU itself (MUFU seeds,
+    shared-memory tables) against NumPy in double precision."""
+    rng = np.random.default_rng(11)
+    x = np.exp2(rng.uniform(-60, 60, 300_000))
+    assert np.abs(engine.device_math("log2_f64", x) - np.log2(x)).max() <= 4e-16 * 60
+    near_one = 1.0 + rng.uniform(-1e-3, 1e-3, 100_000)
+    assert np.abs(engine.device_math("log2_f64", near_one) - np.log2(near_one)).max() <= 3e-16
+    sp = engine.device_math("log2_f64", np.array([0.0, -1.0, np.inf, np.nan, 5e-324]))
+    assert sp[0] == -np.inf and np.isnan(sp[1]) and sp[2] == np.inf and np.isnan(sp[3]) and sp[4] == -1074.0
+
+    e = np.concatenate([rng.uniform(-1019.9, 1019.9, 300_000), rng.uniform(-3, 3, 300_000)])
+    got, ref = engine.device_math("exp2_f64", e), np.exp2(e)
+    assert (np.abs(got - ref) / ref).max() <= 5e-16
+    np.testing.assert_array_equal(engine.device_math("exp2_f64", np.array([-1020.0, -1075.0, -1e9, -np.inf])), 0.0)
+    assert np.isnan(engine.device_math("exp2_f64", np.array([np.nan]))).all()
+
+    r = np.exp(rng.uniform(-20, 20, 200_000))
+    got = engine.device_math("rsqrt_f64", r)
+    assert (np.abs(got * np.sqrt(r) - 1.0)).max() <= 4.5e-16
+
+    for ax in (1.0, -1.0, 0.37, -2.5, 1e-3):
+        yv = np.concatenate([rng.uniform(-3, 3, 100_000), rng.uniform(-1e-3, 1e-3, 20_000), [0.0, ax, -ax]])
+        got = engine.device_math("atan2_abs_f64", yv, aux=ax)
+        assert np.abs(got - np.abs(np.arctan2(yv, ax))).max() <= 9e-16, ax
+        got32 = engine.device_math("atan2_abs_f32", yv, aux=ax)
+        ref32 = np.abs(np.arctan2(yv.astype(np.float32).astype(np.float64), np.float64(np.float32(ax))))
+        assert np.abs(got32 - ref32).max() <= 6e-7, ax
+
+    c = np.linspace(-1, 1, 200_001)
+    assert np.abs(engine.device_math("asin_f32", c) - np.arcsin(c.astype(np.float32).astype(np.float64))).max() <= 2.5e-7
+
+    yy = np.concatenate([rng.uniform(0, 0.1, 100_000), rng.uniform(0, 30, 100_000), [0.0, 25.05, 26.0, 200.0]])
+    y32 = yy.astype(np.float32).astype(np.float64)
+    got = engine.device_math("one_minus_exp2_neg_f32", yy)
+    ref = -np.expm1(-y32 * np.log(2.0))
+    assert (np.abs(got - ref) <= 4e-6 * ref + 1e-12).all()  # relative, also for tiny arguments
+    assert (got[y32 >= 25.05] == 1.0).all()  # the window the kernels skip (kRadialOne) is exactly 1
+
+
 def test_staged_obstime_protocol():
     """zodi_ephemeris_stats(host times) stages them on the device; zodi_evaluate(obstime=NULL) uses
     that copy (same result as passing the times again) and refuses when nothing matching is staged."""

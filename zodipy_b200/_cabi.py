@@ -110,6 +110,7 @@ SYMBOLS = {
                                            C.c_void_p]),
     "zodi_ephemeris_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, c_double_p]),
     "zodi_ephemeris_release_times": (C.c_int, [C.c_void_p]),
+    "zodi_device_math": (C.c_int, [C.c_int, C.c_int32, C.c_int64, c_double_p, C.c_double, c_double_p]),
     "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
     "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
                                        C.c_int64, C.c_int32, C.c_void_p]),

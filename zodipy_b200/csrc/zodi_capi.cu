@@ -1093,6 +1093,30 @@ int64_t zodi_kernel_launch_count(void) { return g_launches.load(); }
 
 double zodi_last_kernel_ms(zodi_model_t m) { return m ? m->last_kernel_ms : 0.0; }
 
+int zodi_device_math(int device, int32_t op, int64_t n, const double* x, double aux, double* y) {
+    if (!x || !y || n < 0) return fail(ZODI_ERR_INVALID, "bad argument");
+    if (op < ZODI_MATH_LOG2_F64 || op > ZODI_MATH_LOG2_F32) return fail(ZODI_ERR_INVALID, "unknown math op %d", op);
+    if (n == 0) return ZODI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    double *d_x = nullptr, *d_y = nullptr;
+    CU_CHECK(cudaMalloc((void**)&d_x, (size_t)n * sizeof(double)));
+    if (cudaMalloc((void**)&d_y, (size_t)n * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_x);
+        return fail(ZODI_ERR_NOMEM, "cannot allocate %lld doubles", (long long)n);
+    }
+    cudaMemcpy(d_x, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    zodi_device_math_kernel<<<grid, 256>>>(op, n, d_x, aux, d_y);
+    g_launches.fetch_add(1);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpy(y, d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_x);
+    cudaFree(d_y);
+    if (err != cudaSuccess) return fail(ZODI_ERR_CUDA, "device math: %s", cudaGetErrorString(err));
+    return ZODI_OK;
+}
+
 int zodi_peak_probe(int device, int32_t kind, double* per_second) {
     if (!per_second) return fail(ZODI_ERR_INVALID, "per_second is NULL");
     int count = 0;

@@ -334,6 +334,31 @@ __global__ void zodi_number_density_kernel(const __grid_constant__ DevModel<doub
     }
 }
 
+// Element-wise device math for tests (zodi_device_math): the routines the integrators are built from,
+// run on the GPU itself (MUFU seeds, shared-memory tables) rather than in the host emulation.
+__global__ void zodi_device_math_kernel(int op, int64_t n, const double* __restrict__ x, double aux,
+                                        double* __restrict__ y) {
+    fp64_tables_stage();
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        double r;
+        switch (op) {
+            case ZODI_MATH_LOG2_F64: r = Math<double>::log2_(v); break;
+            case ZODI_MATH_EXP2_F64: r = Math<double>::exp2_(v); break;
+            case ZODI_MATH_RSQRT_F64: r = Math<double>::rsqrt_(v); break;
+            case ZODI_MATH_ATAN2_ABS_F64: r = Math<double>::atan2_abs_(v, aux); break;
+            case ZODI_MATH_ASIN_F32: r = (double)asin_unit((float)v); break;
+            case ZODI_MATH_ATAN2_ABS_F32: r = (double)Math<float>::atan2_abs_((float)v, (float)aux); break;
+            case ZODI_MATH_ONE_MINUS_EXP2_NEG_F32: r = (double)Math<float>::one_minus_exp2_neg((float)v); break;
+            case ZODI_MATH_EXP2_F32: r = (double)Math<float>::exp2_((float)v); break;
+            case ZODI_MATH_LOG2_F32: r = (double)Math<float>::log2_((float)v); break;
+            default: r = 0.0;
+        }
+        y[i] = r;
+    }
+}
+
 // Spline positions at n times (tests / users): earth_out, obs_out (3, n) or NULL.
 __global__ void zodi_ephemeris_positions_kernel(const __grid_constant__ LaunchArgs a, double* __restrict__ earth_out,
                                                 double* __restrict__ obs_out) {

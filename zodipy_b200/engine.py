@@ -525,6 +525,20 @@ class DeviceMultiBand(DeviceModel):
         return super().evaluate_healpix(nside, obs, earth, return_comps=True, **kwargs)
 
 
+MATH_OPS = {"log2_f64": 0, "exp2_f64": 1, "rsqrt_f64": 2, "atan2_abs_f64": 3, "asin_f32": 4,
+            "atan2_abs_f32": 5, "one_minus_exp2_neg_f32": 6, "exp2_f32": 7, "log2_f32": 8}
+
+
+def device_math(op: str, x, aux: float = 0.0, device: int = 0) -> np.ndarray:
+    """Element-wise device math routine ``op`` (see MATH_OPS) evaluated ON the GPU (test hook)."""
+    lib = _cabi.load()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    y = np.empty_like(x)
+    _cabi.check(lib.zodi_device_math(int(device), MATH_OPS[op], x.size, _cabi.as_double_p(x), float(aux),
+                                     _cabi.as_double_p(y)))
+    return y
+
+
 def kernel_launch_count() -> int:
     return int(_cabi.load().zodi_kernel_launch_count())
 
