@@ -397,6 +397,34 @@ def run_b200(args):
             "api": "Model.evaluate_healpix(nside, obs) -> zodi_evaluate_healpix(ZODI_MEM_HOST): pixel "
                    "directions generated in the kernel prologue, map returned to pinned host memory",
             "max_rel_diff_vs_array_seam": hp_err}
+        # additive SkyCoord-style entry: longitude / latitude (16 B per line of sight) from pinned host
+        # memory, unit vectors + frame rotation formed in the kernel prologue
+        lon_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        lat_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        np.arctan2(u_np[1], u_np[0], out=lon_host.numpy())
+        np.arcsin(np.clip(u_np[2], -1.0, 1.0), out=lat_host.numpy())
+        lon_np, lat_np = lon_host.numpy(), lat_host.numpy()
+        array_seam = out_np.copy()
+        model.evaluate_xyz(u_np, EARTH, EARTH, out=array_seam, out_dtype=out_dtype, outside_flags=flags)
+        for _ in range(2):
+            model.evaluate_lonlat(lon_np, lat_np, EARTH, EARTH, out=out_np, out_dtype=out_dtype, outside_flags=flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            model.evaluate_lonlat(lon_np, lat_np, EARTH, EARTH, out=out_np, out_dtype=out_dtype, outside_flags=flags)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e["lonlat_entry"] = {
+            "value": units_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_e2e,
+            "h2d_bytes_per_step": int(2 * 8 * npix + 6 * 8 * world),
+            "d2h_bytes_per_step": int(npix * out_host.element_size()),
+            "api": "Model.evaluate_lonlat(lon, lat pinned host arrays) -> zodi_evaluate_lonlat(ZODI_MEM_HOST): "
+                   "what Model.evaluate(SkyCoord) calls when the frame is a fixed rotation of the ecliptic",
+            "max_rel_diff_vs_array_seam": float(np.max(np.abs(out_np - array_seam) / np.abs(array_seam)))}
 
     if rank != 0:
         if peer_map is not None:

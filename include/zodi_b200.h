@@ -195,6 +195,24 @@ typedef struct {
     double rot[9];
 } zodi_healpix_args;
 
+/* Evaluation with directions given as spherical sky coordinates, the form a SkyCoord holds them in:
+ * line of sight j points at longitude lon[j], latitude lat[j] [rad] of a frame whose constant
+ * rotation to the mean ecliptic is `rot` (row-major 3x3; identity when has_rot == 0).  The kernel
+ * prologue forms (cos lat cos lon, cos lat sin lon, sin lat) and rotates it, i.e. it replaces
+ * skycoord.transform_to(BarycentricMeanEcliptic).cartesian.xyz (zodipy/model.py:247-251) for every
+ * frame that differs from the mean ecliptic by a fixed rotation (ICRS, Galactic, FK5, ecliptic).
+ * lon / lat: n doubles each in the memory kind of `base` (base.u / base.u_stride are ignored);
+ * everything else in `base` keeps its meaning (per-sample obs / earth, ephemeris + obstime,
+ * peer output, ...).  Host -> device traffic is 16 instead of 24 B per line of sight. */
+typedef struct {
+    zodi_eval_args base;
+    const double* lon;
+    const double* lat;
+    int32_t has_rot;
+    int32_t reserved;
+    double rot[9];
+} zodi_lonlat_args;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int zodi_abi_version(void);
 const char* zodi_last_error(void);
@@ -242,6 +260,12 @@ int zodi_evaluate_healpix(zodi_model_t model, const zodi_healpix_args* args);
 int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_start, int64_t n,
                          const double* rot, double* out, int64_t out_stride, int32_t memory, void* stream);
 
+int zodi_evaluate_lonlat(zodi_model_t model, const zodi_lonlat_args* args);
+/* The unit vectors zodi_evaluate_lonlat integrates along: (3, n) into `out` (row stride out_stride),
+ * lon / lat / out in `memory`; rot may be NULL. */
+int zodi_lonlat_vectors(int device, const double* lon, const double* lat, int64_t n, const double* rot,
+                        double* out, int64_t out_stride, int32_t memory, void* stream);
+
 /* Largest heliocentric observer distance sqrt(x^2+y^2+z^2) over (3, n_obs) observers and the
  * resulting early-out flags; used to form the GLOBAL flags when a job is sharded over GPUs
  * (max-reduce r_max over ranks, then zodi_flags_from_radius). */
@@ -270,6 +294,7 @@ typedef struct zodi_multiband_s* zodi_multiband_t;
 int zodi_multiband_create(const zodi_model_desc* descs, int32_t n_bands, int device, zodi_multiband_t* out);
 int zodi_multiband_evaluate(zodi_multiband_t mb, const zodi_eval_args* args);
 int zodi_multiband_evaluate_healpix(zodi_multiband_t mb, const zodi_healpix_args* args);
+int zodi_multiband_evaluate_lonlat(zodi_multiband_t mb, const zodi_lonlat_args* args);
 int zodi_multiband_destroy(zodi_multiband_t mb);
 
 /* ---- component densities on a set of points -------------------------------------------------

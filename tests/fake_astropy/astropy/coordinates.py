@@ -29,6 +29,8 @@ _ICRS_TO_ECL = np.array([[1, 0, 0], [0, np.cos(_EPS), np.sin(_EPS)], [0, -np.sin
 _ICRS_TO_GAL = np.array([[-0.0548755604, -0.8734370902, -0.4838350155],
                          [0.4941094279, -0.4448296300, 0.7469822445],
                          [-0.8676661490, -0.1980763734, 0.4559837762]])
+_U, _, _VT = np.linalg.svd(_ICRS_TO_GAL)
+_ICRS_TO_GAL = _U @ _VT  # nearest exact rotation to the 10-digit table
 _TO_ECL = {"barycentricmeanecliptic": np.eye(3), "heliocentricmeanecliptic": np.eye(3),
            "icrs": _ICRS_TO_ECL, "galactic": _ICRS_TO_ECL @ _ICRS_TO_GAL.T}
 
@@ -46,16 +48,34 @@ class _Cartesian:
         self.xyz = u.Quantity(xyz, u.AU)
 
 
+class UnitSphericalRepresentation:
+    def __init__(self, lon_rad, lat_rad):
+        self.lon, self.lat = u.Quantity(lon_rad, u.rad), u.Quantity(lat_rad, u.rad)
+
+
+class _FrameInstance(_Frame):
+    def __init__(self, name):
+        self.name = name
+
+    def replicate_without_data(self):
+        return _FrameInstance(self.name)
+
+
 class SkyCoord:
     def __init__(self, lon, lat=None, unit=None, frame=None, obstime=None, _xyz=None, _scalar=None):
         self.frame_name = _frame_name(frame)
+        self.frame = _FrameInstance(self.frame_name)
         self.obstime = obstime
         if _xyz is not None:
             self._xyz, self.isscalar = _xyz, _scalar
+            self.data = _Cartesian(_xyz)
             return
-        lon_r = np.radians(np.asarray(lon.to_value(u.deg) if isinstance(lon, u.Quantity) else lon, dtype=np.float64))
-        lat_r = np.radians(np.asarray(lat.to_value(u.deg) if isinstance(lat, u.Quantity) else lat, dtype=np.float64))
+        if isinstance(lon, u.Quantity):  # angles carry their own unit
+            lon_r, lat_r = np.asarray(lon.to_value(u.rad)), np.asarray(lat.to_value(u.rad))
+        else:
+            lon_r, lat_r = np.radians(np.asarray(lon, dtype=np.float64)), np.radians(np.asarray(lat, dtype=np.float64))
         self.isscalar = lon_r.ndim == 0
+        self.data = UnitSphericalRepresentation(lon_r, lat_r)
         self._xyz = np.array([np.cos(lat_r) * np.cos(lon_r), np.cos(lat_r) * np.sin(lon_r), np.sin(lat_r)])
 
     @property
@@ -74,8 +94,11 @@ class SkyCoord:
                         _scalar=self.isscalar)
 
     def __getitem__(self, item):
-        return SkyCoord(None, frame=self.frame_name, obstime=self.obstime, _xyz=self._xyz[:, item],
-                        _scalar=False)
+        out = SkyCoord(None, frame=self.frame_name, obstime=self.obstime, _xyz=self._xyz[:, item],
+                       _scalar=False)
+        if isinstance(self.data, UnitSphericalRepresentation):
+            out.data = UnitSphericalRepresentation(np.asarray(self.data.lon)[item], np.asarray(self.data.lat)[item])
+        return out
 
 
 def _earth_xyz(mjd):

@@ -257,6 +257,97 @@ def test_evaluate_healpix_equals_array_seam(precision):
     assert model.evaluate_healpix(4, EARTH_20220114, pix_range=(7, 7)).shape == (0,)
 
 
+def _sph2cart(lon, lat):
+    return np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+
+
+def _random_rotation(seed):
+    q, r = np.linalg.qr(np.random.default_rng(seed).normal(size=(3, 3)))
+    q = q * np.sign(np.diag(r))
+    return q * np.sign(np.linalg.det(q))
+
+
+def test_lonlat_vectors_match_host_trigonometry():
+    rng = np.random.default_rng(5)
+    lon = np.concatenate([rng.uniform(-2 * np.pi, 4 * np.pi, 20000), [0.0, np.pi, 2 * np.pi, -np.pi, 1e-300, 7.0, 0.3]])
+    lat = np.concatenate([rng.uniform(-np.pi / 2, np.pi / 2, 20000), [np.pi / 2, -np.pi / 2, 0.0, 1e-17, 0.5, -0.5, 0.0]])
+    np.testing.assert_allclose(engine.lonlat_vectors(lon, lat), _sph2cart(lon, lat), rtol=0, atol=3e-16)
+    rot = _random_rotation(1)
+    np.testing.assert_allclose(engine.lonlat_vectors(lon, lat, rot=rot), rot @ _sph2cart(lon, lat), rtol=0, atol=5e-16)
+    assert engine.lonlat_vectors(np.empty(0), np.empty(0)).shape == (3, 0)
+    with pytest.raises(ValueError):
+        engine.lonlat_vectors(lon, lat[:-1])
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name,x,unit", [("dirbe", 25.0, "um"), ("planck18", 857.0, "GHz"),
+                                         ("rrm-experimental", 60.0, "um")])
+def test_evaluate_lonlat_equals_array_seam(name, x, unit, precision):
+    """Spherical-coordinate entry == array seam fed with the host-built unit vectors: host and device
+    memory, with / without rotation, return_comps, per-sample observers, small and large N
+    (scalar, lanes-per-line-of-sight and packed kernels), and the oracle on a subset."""
+    import torch
+
+    model = zp.Model(zp.Quantity(x, unit), name=name, precision=precision)
+    tol = 1e-12 if precision == "fp64" else 2e-6
+    rng = np.random.default_rng(11)
+    rot = _random_rotation(3)
+    for n in (1, 7, 5000, 700_001):
+        lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+        u = rot @ _sph2cart(lon, lat)
+        ref = model.evaluate_xyz(u, EARTH_20220114, return_comps=True)
+        got = model.evaluate_lonlat(lon, lat, EARTH_20220114, frame_rotation=rot, return_comps=True)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got.sum(axis=0), ref.sum(axis=0), rtol=tol)
+        np.testing.assert_allclose(model.evaluate_lonlat(lon, lat, EARTH_20220114, frame_rotation=rot),
+                                   ref.sum(axis=0), rtol=tol)
+        if n == 5000:
+            ref_o = oracle.evaluate(model.spec, u, EARTH_20220114, EARTH_20220114)
+            assert max_rel_total(got, ref_o) <= TOL[precision][0]
+    # no rotation (ecliptic angles), float32 output, device memory
+    lon, lat = rng.uniform(-np.pi, np.pi, 3000), rng.uniform(-1.5, 1.5, 3000)
+    ref = model.evaluate_xyz(_sph2cart(lon, lat), EARTH_20220114)
+    out32 = model.evaluate_lonlat(lon, lat, EARTH_20220114, out_dtype=np.float32)
+    assert out32.dtype == np.float32
+    np.testing.assert_allclose(out32, ref, rtol=tol + 1e-6)
+    dev = model.evaluate_lonlat(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda(), EARTH_20220114)
+    assert dev.is_cuda
+    np.testing.assert_allclose(dev.cpu().numpy(), ref, rtol=tol)
+    # per-sample observer / Earth positions (time-ordered data through the array seam)
+    ang = rng.uniform(0, 2 * np.pi, 3000)
+    earth = np.array([np.cos(ang), np.sin(ang), np.zeros_like(ang)]) * rng.uniform(0.98, 1.02, 3000)
+    obs = earth * 1.01
+    np.testing.assert_allclose(model.evaluate_lonlat(lon, lat, obs, earth, frame_rotation=rot),
+                               model.evaluate_xyz(rot @ _sph2cart(lon, lat), obs, earth), rtol=tol)
+    assert model.evaluate_lonlat(np.empty(0), np.empty(0), EARTH_20220114).shape == (0,)
+    with pytest.raises(ValueError):
+        model.evaluate_lonlat(lon, lat[:-1], EARTH_20220114)
+
+
+def test_evaluate_lonlat_with_device_ephemeris_and_multiband():
+    n = 20000
+    rng = np.random.default_rng(4)
+    knots = 59000.0 + np.arange(0, 24 * 12 + 1) / 24.0
+    ang = 2 * np.pi * (knots - 59000.0) / 365.25
+    earth_knots = np.array([np.cos(ang), np.sin(ang), 1e-3 * np.sin(3 * ang)])
+    eph = engine.DeviceEphemeris(float(knots[0]), float(knots[1] - knots[0]), earth_knots, device=0)
+    t = np.sort(rng.uniform(knots[0], knots[-1], n))
+    lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+    rot = _random_rotation(9)
+    u = rot @ _sph2cart(lon, lat)
+    for precision, tol in (("fp64", 1e-12), ("fp32", 2e-6)):
+        model = zp.Model(zp.Quantity(25.0, "um"), precision=precision)
+        for observer in ("earth", "semb-l2"):
+            ref = model.evaluate_tod_xyz(u, t, eph, observer=observer)
+            got = model.evaluate_lonlat(lon, lat, frame_rotation=rot, ephemeris=eph, obstime=t, observer=observer)
+            np.testing.assert_allclose(got, ref, rtol=tol)
+    mb = zp.MultiBandModel([zp.Quantity(v, "um") for v in (12.0, 25.0, 60.0)], name="dirbe", precision="fp32")
+    ref = mb.evaluate_xyz(u, EARTH_20220114)
+    got = mb.device_model.evaluate_lonlat(lon, lat, EARTH_20220114, rot=rot, precision="fp32")
+    assert got.shape == (3, n)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
+
+
 @pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um"),
                                          ("planck13", 545.0, "GHz"), ("dirbe", 1.25, "um"),
                                          ("dirbe", 3.5, "um")])  # the last two: scattering

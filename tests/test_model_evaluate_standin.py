@@ -43,7 +43,17 @@ def oracle_seam(monkeypatch):
         em = oracle.evaluate(self.spec, np.asarray(unit_vectors), np.asarray(obs_xyz), np.asarray(earth))
         return em if return_comps else em.sum(axis=0)
 
+    def lonlat_seam(self, lon, lat, obs_xyz=None, earth_xyz=None, *, frame_rotation=None, return_comps=False,
+                    **kwargs):
+        assert kwargs.get("ephemeris") is None
+        lon, lat = np.asarray(lon), np.asarray(lat)
+        u = np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+        if frame_rotation is not None:
+            u = np.asarray(frame_rotation) @ u
+        return seam(self, u, obs_xyz, earth_xyz, return_comps=return_comps)
+
     monkeypatch.setattr(zp.Model, "evaluate_xyz", seam)
+    monkeypatch.setattr(zp.Model, "evaluate_lonlat", lonlat_seam)
 
 
 def _dirbe_table_check(ap, rel):
@@ -121,6 +131,35 @@ def test_shapes_and_return_comps(ap, oracle_seam):
     assert np.all(np.asarray(far) < np.asarray(total))  # fainter from 1.5 AU (docs/usage.md:199)
 
 
+def test_sky_rotation_is_read_off_the_frame_transformation(ap, oracle_seam):
+    """Model(sky_rotation="device") ships SkyCoord angles + one 3x3 matrix (taken from the frame
+    transformation itself) instead of host-transformed unit vectors; same results as "host"."""
+    import zodipy_b200 as zp
+    from zodipy_b200 import astro
+
+    units, time, coords = ap
+    t = time.Time("2021-01-01T00:00:00")
+    rng = np.random.default_rng(3)
+    lon, lat = rng.uniform(0, 360, 50), rng.uniform(-90, 90, 50)
+    for frame in ("galactic", "icrs", coords.BarycentricMeanEcliptic):
+        sc = coords.SkyCoord(lon, lat, unit=units.deg, obstime=t, frame=frame)
+        got = astro.sky_lonlat_rotation(sc)
+        assert got is not None
+        lon_r, lat_r, rot = got
+        np.testing.assert_allclose(lon_r, np.radians(lon), rtol=0, atol=1e-15)
+        u = rot @ np.array([np.cos(lat_r) * np.cos(lon_r), np.cos(lat_r) * np.sin(lon_r), np.sin(lat_r)])
+        np.testing.assert_allclose(u, astro.sky_unit_vectors(sc), rtol=0, atol=1e-15)
+        dev = zp.Model(25 * units.micron, sky_rotation="device").evaluate(sc, return_comps=True)
+        host = zp.Model(25 * units.micron, sky_rotation="host").evaluate(sc, return_comps=True)
+        np.testing.assert_allclose(np.asarray(dev), np.asarray(host), rtol=1e-12)
+    # a coordinate that is not a pure direction in a known frame -> host transformation
+    moved = coords.SkyCoord(lon, lat, unit=units.deg, obstime=t, frame="galactic").transform_to("icrs")
+    assert astro.sky_lonlat_rotation(moved) is None or isinstance(moved.data, coords.UnitSphericalRepresentation)
+    assert zp.Model(25 * units.micron).evaluate(moved).shape == (50,)
+    with pytest.raises(ValueError):
+        zp.Model(25 * units.micron, sky_rotation="gpu")
+
+
 def test_time_ordered_inputs(ap, oracle_seam):
     import zodipy_b200 as zp
 
@@ -165,6 +204,26 @@ def test_tod_device_ephemeris_equals_host_path_gpu(ap, obspos):
     np.testing.assert_allclose(np.asarray(dev), np.asarray(host), rtol=1e-11, atol=1e-30)
     with pytest.raises(ValueError):
         zp.Model(25 * units.micron, tod_ephemeris="device").evaluate(sc, obspos="not-a-body")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tod", [False, True])
+def test_sky_rotation_device_equals_host_gpu(ap, tod):
+    """SkyCoord angles rotated in the kernel prologue == Astropy-transformed unit vectors, real kernels."""
+    import zodipy_b200 as zp
+
+    units, time, coords = ap
+    n = 4000
+    rng = np.random.default_rng(8)
+    times = time.Time(59215.0 + np.linspace(0, 20, n), format="mjd") if tod else time.Time("2021-01-01T00:00:00")
+    for frame in ("galactic", "icrs", coords.BarycentricMeanEcliptic):
+        sc = coords.SkyCoord(rng.uniform(0, 360, n), rng.uniform(-90, 90, n), unit=units.deg, obstime=times,
+                             frame=frame)
+        for kw in ({}, {"tod_ephemeris": "device"}):
+            host = zp.Model(25 * units.micron, sky_rotation="host", **kw).evaluate(sc, obspos="semb-l2")
+            dev = zp.Model(25 * units.micron, sky_rotation="device", **kw).evaluate(sc, obspos="semb-l2")
+            assert dev.shape == (n,)
+            np.testing.assert_allclose(np.asarray(dev), np.asarray(host), rtol=1e-11)
 
 
 @pytest.mark.gpu

@@ -91,6 +91,15 @@ class HealpixArgs(C.Structure):
     ]
 
 
+class LonLatArgs(C.Structure):
+    _fields_ = [
+        ("base", EvalArgs),
+        ("lon", C.c_void_p), ("lat", C.c_void_p),
+        ("has_rot", C.c_int32), ("reserved", C.c_int32),
+        ("rot", C.c_double * 9),
+    ]
+
+
 # every symbol include/zodi_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "zodi_abi_version": (C.c_int, []),
@@ -114,6 +123,10 @@ SYMBOLS = {
     "zodi_evaluate_healpix": (C.c_int, [C.c_void_p, C.POINTER(HealpixArgs)]),
     "zodi_healpix_vectors": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, c_double_p, C.c_void_p,
                                        C.c_int64, C.c_int32, C.c_void_p]),
+    "zodi_evaluate_lonlat": (C.c_int, [C.c_void_p, C.POINTER(LonLatArgs)]),
+    "zodi_lonlat_vectors": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, c_double_p, C.c_void_p, C.c_int64,
+                                      C.c_int32, C.c_void_p]),
+    "zodi_multiband_evaluate_lonlat": (C.c_int, [C.c_void_p, C.POINTER(LonLatArgs)]),
     "zodi_max_observer_radius": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                            C.c_void_p, c_double_p]),
     "zodi_flags_from_radius": (C.c_int, [C.c_void_p, C.c_double, c_uint8_p]),

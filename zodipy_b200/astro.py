@@ -45,8 +45,54 @@ def semb_l2(earthpos):
     return earthpos / dist * (dist + MEAN_DIST_TO_L2)
 
 
-def prepare_arrays(skycoord, obspos, obspos_isstr, interp_obstimes, ephemeris):
-    """(earth_xyz, obs_xyz, unit_vectors) as the array seam expects (``model.py:212-251``)."""
+_PROBE_LON = np.array([0.0, 0.5 * np.pi, 0.0, 0.7, 4.1])
+_PROBE_LAT = np.array([0.0, 0.0, 0.5 * np.pi, -0.4, 1.1])
+
+
+def sky_lonlat_rotation(skycoord):
+    """``(lon, lat, R)`` with the mean-ecliptic unit vectors equal to
+    ``R @ (cos lat cos lon, cos lat sin lon, sin lat)``, or ``None``.
+
+    ``skycoord.transform_to(BarycentricMeanEcliptic).cartesian.xyz`` (``model.py:247-251``) is, for
+    direction-only coordinates in ICRS / Galactic / FK5 / mean-ecliptic frames, a fixed rotation of
+    the sphere.  R is read off Astropy itself by transforming the three axes of the input frame,
+    and two more probe directions verify that the transformation really is that rotation (frames
+    with aberration, per-sample frame attributes or distances fail the check or raise, and the
+    caller falls back to transforming every coordinate on the host).  The angles then go to the
+    device as they are (16 B per line of sight) and the kernel prologue does the trigonometry.
+    """
+    try:
+        data = skycoord.data
+        if not isinstance(data, coords.UnitSphericalRepresentation):
+            return None
+        lon = np.ascontiguousarray(np.atleast_1d(data.lon.to_value(units.rad)), dtype=np.float64).reshape(-1)
+        lat = np.ascontiguousarray(np.atleast_1d(data.lat.to_value(units.rad)), dtype=np.float64).reshape(-1)
+        frame = skycoord.frame.replicate_without_data()
+        probe = coords.SkyCoord(_PROBE_LON * units.rad, _PROBE_LAT * units.rad, frame=frame)
+        xyz = np.asarray(probe.transform_to(coords.BarycentricMeanEcliptic).cartesian.xyz.value, dtype=np.float64)
+    except Exception:  # anything unusual about the frame: keep the reference's host transformation
+        return None
+    rot = np.ascontiguousarray(xyz[:, :3])  # columns = images of the frame's x, y, z axes
+    cl = np.cos(_PROBE_LAT[3:])
+    src = np.array([cl * np.cos(_PROBE_LON[3:]), cl * np.sin(_PROBE_LON[3:]), np.sin(_PROBE_LAT[3:])])
+    if not (np.allclose(rot.T @ rot, np.eye(3), rtol=0, atol=1e-12)
+            and np.allclose(rot @ src, xyz[:, 3:], rtol=0, atol=1e-12)):
+        return None
+    return lon, lat, rot
+
+
+def sky_unit_vectors(skycoord):
+    """Mean-ecliptic unit vectors (3, N) computed by Astropy on the host (``model.py:247-251``)."""
+    ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
+    u_xyz = ecl.cartesian.xyz.value
+    if ecl.isscalar:
+        u_xyz = u_xyz[:, np.newaxis]
+    return np.ascontiguousarray(u_xyz)
+
+
+def prepare_arrays(skycoord, obspos, obspos_isstr, interp_obstimes, ephemeris, with_directions=True):
+    """(earth_xyz, obs_xyz, unit_vectors) as the array seam expects (``model.py:212-251``);
+    ``unit_vectors`` is ``None`` when ``with_directions`` is false (lon / lat go to the device)."""
     if interp_obstimes is None:
         earth_xyz = _body_xyz("earth", skycoord.obstime, ephemeris).flatten()
     else:
@@ -77,18 +123,14 @@ def prepare_arrays(skycoord, obspos, obspos_isstr, interp_obstimes, ephemeris):
     if earth_xyz.ndim == 1:
         earth_xyz = earth_xyz[:, np.newaxis]
 
-    ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
-    u_xyz = ecl.cartesian.xyz.value
-    if ecl.isscalar:
-        u_xyz = u_xyz[:, np.newaxis]
-    return earth_xyz, obs_xyz, np.ascontiguousarray(u_xyz)
+    return earth_xyz, obs_xyz, (sky_unit_vectors(skycoord) if with_directions else None)
 
 
 def as_mjy_per_sr(emission):
     return emission << (units.MJy / units.sr)
 
 
-def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device):
+def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device, with_directions=True):
     """Hourly Earth (and observer-body) knots as a device-resident spline
     (:class:`zodipy_b200.engine.DeviceEphemeris`) for time-ordered data with a string ``obspos``.
 
@@ -113,6 +155,5 @@ def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device):
     # use the array's own spacing so the device knots equal the reference's knot times bit for bit
     delta = float(knots_mjd[1] - knots_mjd[0])
     eph = DeviceEphemeris(float(knots_mjd[0]), delta, earth_knots, obs_knots, device=device)
-    ecl = skycoord.transform_to(coords.BarycentricMeanEcliptic)
-    u_xyz = np.ascontiguousarray(ecl.cartesian.xyz.value)
+    u_xyz = sky_unit_vectors(skycoord) if with_directions else None
     return eph, mode, u_xyz, np.ascontiguousarray(skycoord.obstime.mjd, dtype=np.float64)

@@ -439,6 +439,7 @@ void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
     la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0;
     set_ephemeris(la, nullptr, nullptr);
     la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0; la.hp_nest = 0;
+    la.lon = nullptr; la.lat = nullptr;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = 0.0;
     if (!hp) return;
     la.hp_nside = hp->nside;
@@ -446,6 +447,14 @@ void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
     la.hp_rotate = hp->has_rot != 0;
     la.hp_nest = hp->nest != 0;
     for (int i = 0; i < 9; ++i) la.hp_rot[i] = hp->rot[i];
+}
+
+// Directions from spherical coordinates (after set_healpix(la, nullptr, ..)): device pointers.
+void set_lonlat(LaunchArgs& la, const zodi_lonlat_args* ll, const double* d_lon, const double* d_lat) {
+    if (!ll) return;
+    la.lon = d_lon; la.lat = d_lat;
+    la.hp_rotate = ll->has_rot != 0;
+    for (int i = 0; i < 9; ++i) la.hp_rot[i] = ll->rot[i];
 }
 
 // ---- host-memory path: chunked, 3-deep pipeline H2D | kernel | D2H on private streams ------
@@ -463,7 +472,8 @@ int ensure_workspace(zodi_model_s* m, int64_t chunk) {
     return ZODI_OK;
 }
 
-int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const zodi_healpix_args* hp) {
+int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const zodi_healpix_args* hp,
+                  const zodi_lonlat_args* ll) {
     std::lock_guard<std::mutex> lock(m->ws_mutex);
     const int64_t n = a->n;
     int64_t chunk = 1 << 20;
@@ -489,7 +499,11 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         double* d_obs = s.d_in + 3 * m->ws_chunk;
         double* d_earth = s.d_in + 6 * m->ws_chunk;
         const size_t pitch = (size_t)m->ws_chunk * sizeof(double);
-        if (!hp)
+        if (ll) {  // 16 B per line of sight instead of 24: rows 0 / 1 of the direction slot
+            CU_CHECK(cudaMemcpyAsync(d_u, ll->lon + done, (size_t)cn * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+            CU_CHECK(cudaMemcpyAsync(d_u + m->ws_chunk, ll->lat + done, (size_t)cn * sizeof(double),
+                                     cudaMemcpyHostToDevice, s.stream));
+        } else if (!hp)
             CU_CHECK(cudaMemcpy2DAsync(d_u, pitch, a->u + done, (size_t)a->u_stride * sizeof(double),
                                        (size_t)cn * sizeof(double), 3, cudaMemcpyHostToDevice, s.stream));
         const double* d_time = d_obs;
@@ -519,6 +533,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
         la.out = s.d_out; la.out_stride = m->ws_chunk;
         la.n_peers = 0; la.peer_offset = 0; la.peer_stride = 0;
         set_healpix(la, hp, done);
+        set_lonlat(la, ll, d_u, d_u + m->ws_chunk);
         if (a->ephemeris) set_ephemeris(la, a->ephemeris, d_time);
         if (!s.used) CU_CHECK(cudaEventRecord(s.k0, s.stream));
         CU_CHECK(launch_eval(m, la, a->precision, s.stream));
@@ -629,9 +644,11 @@ int zodi_max_observer_radius(zodi_model_t m, const double* obs, int64_t n_obs, i
     return max_r_device(m, obs, n_obs, obs_stride, (cudaStream_t)stream, r_max);
 }
 
-static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_healpix_args* hp) {
-    int rc = check_args(m, a, hp == nullptr);
+static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_healpix_args* hp,
+                         const zodi_lonlat_args* ll = nullptr) {
+    int rc = check_args(m, a, hp == nullptr && ll == nullptr);
     if (rc) return rc;
+    if (ll && a->n > 0 && (!ll->lon || !ll->lat)) return fail(ZODI_ERR_INVALID, "lon/lat must be non-NULL");
     if (a->n == 0) return ZODI_OK;
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", m->device);
@@ -651,7 +668,7 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
     }
     const uint32_t mask = flags_to_mask(flags, m->desc.n_comps);
 
-    if (a->memory == ZODI_MEM_HOST) return evaluate_host(m, a, mask, hp);
+    if (a->memory == ZODI_MEM_HOST) return evaluate_host(m, a, mask, hp, ll);
 
     LaunchArgs la;
     la.n = a->n;
@@ -666,6 +683,7 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
     la.n_peers = a->n_peers; la.peer_offset = a->peer_offset; la.peer_stride = a->peer_stride;
     for (int p = 0; p < ZODI_MAX_PEERS; ++p) la.peer_out[p] = p < a->n_peers ? a->peer_out[p] : nullptr;
     set_healpix(la, hp, 0);
+    if (ll) set_lonlat(la, ll, ll->lon, ll->lat);
     if (a->ephemeris) set_ephemeris(la, a->ephemeris, a->obstime);
     la.cyc_block = a->cyclic_block; la.cyc_parts = a->cyclic_parts; la.cyc_rank = a->cyclic_rank;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
@@ -894,6 +912,52 @@ int zodi_healpix_vectors(int device, int64_t nside, int32_t nest, int64_t ipix_s
     return ZODI_OK;
 }
 
+// ---- directions from spherical sky coordinates ---------------------------------------------------
+int zodi_evaluate_lonlat(zodi_model_t m, const zodi_lonlat_args* ll) {
+    if (!ll) return fail(ZODI_ERR_INVALID, "lonlat args are NULL");
+    return evaluate_impl(m, &ll->base, nullptr, ll);
+}
+
+int zodi_lonlat_vectors(int device, const double* lon, const double* lat, int64_t n, const double* rot,
+                        double* out, int64_t out_stride, int32_t memory, void* stream) {
+    if (n < 0 || !out || out_stride < n || (n > 0 && (!lon || !lat))) return fail(ZODI_ERR_INVALID, "bad argument");
+    if (memory != ZODI_MEM_HOST && memory != ZODI_MEM_DEVICE) return fail(ZODI_ERR_INVALID, "unknown memory kind");
+    if (n == 0) return ZODI_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    LaunchArgs la;
+    std::memset(&la, 0, sizeof(la));
+    la.n = n;
+    set_healpix(la, nullptr, 0);
+    zodi_lonlat_args ll;
+    std::memset(&ll, 0, sizeof(ll));
+    ll.has_rot = rot != nullptr;
+    if (rot) std::memcpy(ll.rot, rot, sizeof(ll.rot));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d_buf = nullptr;  // host memory: [lon | lat | out(3, n)] staged in one allocation
+    double* d_out = out;
+    const double *d_lon = lon, *d_lat = lat;
+    if (memory == ZODI_MEM_HOST) {
+        st = nullptr;
+        CU_CHECK(cudaMalloc((void**)&d_buf, (size_t)5 * n * sizeof(double)));
+        cudaError_t e = cudaMemcpy(d_buf, lon, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_buf + n, lat, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(d_buf); return fail(ZODI_ERR_CUDA, "lonlat upload failed: %s", cudaGetErrorString(e)); }
+        d_lon = d_buf; d_lat = d_buf + n; d_out = d_buf + 2 * n;
+    }
+    set_lonlat(la, &ll, d_lon, d_lat);
+    const int64_t ld = memory == ZODI_MEM_HOST ? n : out_stride;
+    zodi_healpix_vectors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(la, d_out, ld);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && memory == ZODI_MEM_HOST)
+        e = cudaMemcpy2D(out, (size_t)out_stride * sizeof(double), d_out, (size_t)n * sizeof(double),
+                         (size_t)n * sizeof(double), 3, cudaMemcpyDeviceToHost);
+    if (d_buf) cudaFree(d_buf);
+    if (e != cudaSuccess) return fail(ZODI_ERR_CUDA, "lonlat vectors failed: %s", cudaGetErrorString(e));
+    return ZODI_OK;
+}
+
 // ---- multi-band ------------------------------------------------------------------------------
 struct zodi_multiband_s { zodi_model_s* model; };
 
@@ -988,6 +1052,11 @@ int zodi_multiband_evaluate(zodi_multiband_t mb, const zodi_eval_args* a) {
 int zodi_multiband_evaluate_healpix(zodi_multiband_t mb, const zodi_healpix_args* hp) {
     if (!mb) return fail(ZODI_ERR_INVALID, "multi-band handle is NULL");
     return zodi_evaluate_healpix(mb->model, hp);
+}
+
+int zodi_multiband_evaluate_lonlat(zodi_multiband_t mb, const zodi_lonlat_args* ll) {
+    if (!mb) return fail(ZODI_ERR_INVALID, "multiband handle is NULL");
+    return zodi_evaluate_lonlat(mb->model, ll);
 }
 
 int zodi_multiband_destroy(zodi_multiband_t mb) {

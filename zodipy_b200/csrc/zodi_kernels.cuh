@@ -36,7 +36,9 @@ struct LaunchArgs {
     // on-device directions: HEALPix RING pixel hp_start + j (u is ignored when hp_nside > 0)
     int64_t hp_nside;     int64_t hp_start;
     int hp_nest;          // 1: hp_start + j is a NESTED index (converted to RING on the fly)
-    int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel vector
+    int hp_rotate;        double hp_rot[9];   // row-major 3x3 applied to the pixel / lon-lat vector
+    // on-device directions from spherical sky coordinates [rad] (u is ignored when lon != NULL)
+    const double* lon;    const double* lat;
     // block-cyclic shard layout (see zodi_eval_args.cyclic_block); 0 = identity
     int64_t cyc_block;    int cyc_parts;      int cyc_rank;
     // on-device ephemeris (time-ordered data): positions from cubic splines at obstime[j]
@@ -90,20 +92,28 @@ __device__ __forceinline__ int64_t global_index(const LaunchArgs& a, int64_t j) 
 // Direction of line of sight j: loaded (reference array seam) or generated from the pixel index.
 __device__ __forceinline__ void load_direction(const LaunchArgs& a, int64_t jj, double& ux, double& uy,
                                                double& uz) {
+    if (a.hp_nside <= 0 && a.lon == nullptr) {
+        ux = a.u[jj]; uy = a.u[a.u_stride + jj]; uz = a.u[2 * a.u_stride + jj];
+        return;
+    }
+    double x, y, z;
     if (a.hp_nside > 0) {
-        double x, y, z;
         long long ipix = a.hp_start + global_index(a, jj);
         if (a.hp_nest) ipix = healpix_nest2ring(a.hp_nside, ipix);
         healpix_ring_pix2vec(a.hp_nside, ipix, x, y, z);
-        if (a.hp_rotate) {
-            ux = a.hp_rot[0] * x + a.hp_rot[1] * y + a.hp_rot[2] * z;
-            uy = a.hp_rot[3] * x + a.hp_rot[4] * y + a.hp_rot[5] * z;
-            uz = a.hp_rot[6] * x + a.hp_rot[7] * y + a.hp_rot[8] * z;
-        } else {
-            ux = x; uy = y; uz = z;
-        }
     } else {
-        ux = a.u[jj]; uy = a.u[a.u_stride + jj]; uz = a.u[2 * a.u_stride + jj];
+        // UnitSphericalRepresentation -> cartesian, as SkyCoord.cartesian does on the host
+        double sl, cl, sb, cb;
+        sincos(a.lon[jj], &sl, &cl);
+        sincos(a.lat[jj], &sb, &cb);
+        x = cb * cl; y = cb * sl; z = sb;
+    }
+    if (a.hp_rotate) {
+        ux = a.hp_rot[0] * x + a.hp_rot[1] * y + a.hp_rot[2] * z;
+        uy = a.hp_rot[3] * x + a.hp_rot[4] * y + a.hp_rot[5] * z;
+        uz = a.hp_rot[6] * x + a.hp_rot[7] * y + a.hp_rot[8] * z;
+    } else {
+        ux = x; uy = y; uz = z;
     }
 }
 
@@ -307,7 +317,7 @@ zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
         });
 }
 
-// Pixel-centre unit vectors only (same device routine the integrator uses in its prologue).
+// Generated directions only (same device routine the integrators use in their prologue).
 __global__ void zodi_healpix_vectors_kernel(const __grid_constant__ LaunchArgs args, double* __restrict__ out,
                                             int64_t out_stride) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -46,6 +46,42 @@ def _rows(a, name: str):
     return a, a.ctypes.data, a.shape[1], stride
 
 
+def _vec(a, name: str):
+    """(array, data_ptr, n) of a contiguous 1-D float64 array (NumPy or torch CUDA)."""
+    if _is_torch(a):
+        import torch
+
+        if a.dtype != torch.float64:
+            raise ValueError(f"{name} must be float64")
+        a = a.reshape(-1).contiguous()
+        return a, a.data_ptr(), a.shape[0]
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    return a, a.ctypes.data, a.size
+
+
+class _LonLat:
+    """Directions given as spherical coordinates [rad] + optional 3x3 rotation to the mean ecliptic."""
+
+    def __init__(self, lon, lat, rot=None):
+        if _is_torch(lon) != _is_torch(lat):
+            raise ValueError("lon and lat must both be NumPy arrays or both torch CUDA tensors")
+        self.lon, self.lon_ptr, self.n = _vec(lon, "lon")
+        self.lat, self.lat_ptr, n_lat = _vec(lat, "lat")
+        if n_lat != self.n:
+            raise ValueError("lon and lat must have the same length")
+        self.rot = None if rot is None else np.ascontiguousarray(np.asarray(rot, dtype=np.float64).reshape(9))
+
+    def pack(self, base):
+        ll = _cabi.LonLatArgs()
+        ll.base = base
+        ll.lon, ll.lat = self.lon_ptr, self.lat_ptr
+        if self.rot is not None:
+            ll.has_rot = 1
+            for i in range(9):
+                ll.rot[i] = float(self.rot[i])
+        return ll
+
+
 MEAN_DIST_TO_L2 = 0.009896235034000056  # AU, zodipy/bodies.py:13
 
 
@@ -202,8 +238,11 @@ class DeviceModel:
 
     def evaluate(self, u, obs=None, earth=None, *, return_comps: bool = False, precision: str = "fp64",
                  out=None, out_dtype=None, outside_flags=None, peer_map=None, ephemeris=None,
-                 obstime=None, observer: str = "earth"):
+                 obstime=None, observer: str = "earth", lonlat=None):
         """Emission [MJy/sr] for unit vectors ``u`` (3, N).
+
+        ``lonlat``: a :class:`_LonLat` (see :meth:`evaluate_lonlat`); ``u`` is then ``None`` and the
+        unit vectors are formed (and rotated to the ecliptic) in the kernel prologue.
 
         ``obs`` / ``earth``: (3,), (3, 1) or (3, N) [AU]; ``earth`` defaults to ``obs``.
         ``outside_flags``: optional (ncomps, 2) uint8 GLOBAL early-out flags (needed when the
@@ -219,11 +258,15 @@ class DeviceModel:
         """
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
-        device_mem = _is_torch(u)
-        u_a, u_ptr, n, u_stride = _rows(u, "unit_vectors")
+        if lonlat is not None:
+            device_mem = _is_torch(lonlat.lon)
+            u_a, u_ptr, n, u_stride = lonlat.lon, None, lonlat.n, 0
+        else:
+            device_mem = _is_torch(u)
+            u_a, u_ptr, n, u_stride = _rows(u, "unit_vectors")
         if ephemeris is not None:
             return self._evaluate_tod(u_a, u_ptr, n, u_stride, device_mem, ephemeris, obstime, observer,
-                                      return_comps, precision, out, out_dtype, outside_flags)
+                                      return_comps, precision, out, out_dtype, outside_flags, lonlat)
         if obs is None:
             raise ValueError("obs is required unless an ephemeris is given")
         if earth is None:
@@ -307,11 +350,28 @@ class DeviceModel:
             args.peer_offset, args.peer_stride = peer_map.offset, peer_map.n_total
             if peer_map.cyclic is not None:
                 args.cyclic_block, args.cyclic_parts, args.cyclic_rank = peer_map.cyclic
-        _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
+        self._dispatch(args, lonlat)
         return out
 
+    def _dispatch(self, args, lonlat) -> None:
+        if lonlat is None:
+            _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
+        else:
+            _cabi.check(self._lib.zodi_evaluate_lonlat(self._handle, C.byref(lonlat.pack(args))))
+
+    def evaluate_lonlat(self, lon, lat, obs=None, earth=None, *, rot=None, **kwargs):
+        """Emission for directions given as longitude / latitude [rad] (N,) of a frame whose constant
+        rotation to the mean ecliptic is the 3x3 ``rot`` (``None``: the angles are ecliptic).
+
+        The unit vectors ``rot @ (cos lat cos lon, cos lat sin lon, sin lat)`` are formed in the
+        kernel prologue, so 16 instead of 24 B per line of sight are uploaded and the host never
+        builds the (3, N) array.  All keyword arguments of :meth:`evaluate` apply (per-sample
+        ``obs`` / ``earth``, ``ephemeris`` + ``obstime``, ``peer_map``, ...).
+        """
+        return self.evaluate(None, obs, earth, lonlat=_LonLat(lon, lat, rot), **kwargs)
+
     def _evaluate_tod(self, u_a, u_ptr, n, u_stride, device_mem, ephemeris, obstime, observer,
-                      return_comps, precision, out, out_dtype, outside_flags):
+                      return_comps, precision, out, out_dtype, outside_flags, lonlat=None):
         if obstime is None:
             raise ValueError("obstime is required with an ephemeris")
         if ephemeris.device != self.device:
@@ -357,7 +417,7 @@ class DeviceModel:
         # integrates from that copy, so they cross the bus once
         staged = not device_mem and not os.environ.get("ZODI_TOD_EXPLICIT_OBSTIME")  # env: A/B measurement only
         args.ephemeris, args.obstime = ephemeris._handle, (None if staged else t_ptr)
-        _cabi.check(self._lib.zodi_evaluate(self._handle, C.byref(args)))
+        self._dispatch(args, lonlat)
         return out
 
     def evaluate_healpix(self, nside: int, obs, earth=None, *, pix_range=None, rot=None, nest: bool = False,
@@ -524,6 +584,11 @@ class DeviceMultiBand(DeviceModel):
         kwargs.pop("return_comps", None)
         return super().evaluate_healpix(nside, obs, earth, return_comps=True, **kwargs)
 
+    def evaluate_lonlat(self, lon, lat, obs=None, earth=None, *, rot=None, **kwargs):
+        kwargs.pop("return_comps", None)
+        return DeviceModel.evaluate(self, None, obs, earth, lonlat=_LonLat(lon, lat, rot), return_comps=True,
+                                    **kwargs)
+
 
 MATH_OPS = {"log2_f64": 0, "exp2_f64": 1, "rsqrt_f64": 2, "atan2_abs_f64": 3, "asin_f32": 4,
             "atan2_abs_f32": 5, "one_minus_exp2_neg_f32": 6, "exp2_f32": 7, "log2_f32": 8}
@@ -554,6 +619,16 @@ def healpix_vectors(nside: int, pix_range=None, rot=None, device: int = 0, nest:
         rot_p = _cabi.as_double_p(rot_a)
     _cabi.check(_cabi.load().zodi_healpix_vectors(int(device), nside, int(bool(nest)), lo, hi - lo, rot_p, out.ctypes.data,
                                                   max(hi - lo, 1), _cabi.MEM_HOST, None))
+    return out
+
+
+def lonlat_vectors(lon, lat, rot=None, device: int = 0) -> np.ndarray:
+    """(3, n) unit vectors the lon / lat entry integrates along, computed by the device routine."""
+    ll = _LonLat(np.asarray(lon, dtype=np.float64), np.asarray(lat, dtype=np.float64), rot)
+    out = np.empty((3, ll.n), dtype=np.float64)
+    rot_p = None if ll.rot is None else _cabi.as_double_p(ll.rot)
+    _cabi.check(_cabi.load().zodi_lonlat_vectors(int(device), ll.lon_ptr, ll.lat_ptr, ll.n, rot_p, out.ctypes.data,
+                                                 max(ll.n, 1), _cabi.MEM_HOST, None))
     return out
 
 

@@ -10,7 +10,10 @@ sharding use.
 Additive, defaulted knobs (not in the reference): ``precision`` ("fp64" faithful | "fp32" fast),
 ``device`` (CUDA ordinal; default ``LOCAL_RANK`` or 0), ``tod_ephemeris`` ("host": per-sample
 positions interpolated with SciPy as in the reference | "device": hourly knots uploaded once and
-interpolated in the kernel prologue).  ``nprocesses`` is accepted for API
+interpolated in the kernel prologue), ``sky_rotation`` ("device": SkyCoord longitudes /
+latitudes are uploaded as they are and the rotation to the mean ecliptic happens in the kernel
+prologue whenever Astropy's transformation of the frame is a fixed rotation | "host": every
+coordinate is transformed by Astropy as in the reference).  ``nprocesses`` is accepted for API
 compatibility and ignored: the GPU path has no use for host worker processes.
 """
 from __future__ import annotations
@@ -33,7 +36,7 @@ class Model:
     def __init__(self, x, *, weights=None, name: str = "dirbe", gauss_quad_degree: int = 50,
                  extrapolate: bool = False, ephemeris: str = "builtin",
                  precision: str = "fp64", device: int | None = None,
-                 tod_ephemeris: str = "host") -> None:
+                 tod_ephemeris: str = "host", sky_rotation: str = "device") -> None:
         try:
             if not x.isscalar and weights is None:
                 raise ValueError("Bandpass weights must be provided for non-scalar `x`.")
@@ -63,7 +66,10 @@ class Model:
             raise ValueError("precision must be 'fp64' or 'fp32'")
         if tod_ephemeris not in ("host", "device"):
             raise ValueError("tod_ephemeris must be 'host' or 'device'")
+        if sky_rotation not in ("host", "device"):
+            raise ValueError("sky_rotation must be 'host' or 'device'")
         self._tod_ephemeris = tod_ephemeris
+        self._sky_rotation = sky_rotation
         self._x = x
         self._bounds_error = not extrapolate
         self._normalized_weights = normalized_weights
@@ -128,6 +134,20 @@ class Model:
             unit_vectors, return_comps=return_comps, precision=precision or self._precision, out=out,
             out_dtype=out_dtype, ephemeris=ephemeris, obstime=obstime, observer=observer)
 
+    def evaluate_lonlat(self, lon, lat, obs_xyz=None, earth_xyz=None, *, frame_rotation=None,
+                        return_comps: bool = False, precision: str | None = None, out=None, out_dtype=None,
+                        outside_flags=None, ephemeris=None, obstime=None, observer: str = "earth"):
+        """Like ``evaluate_xyz`` / ``evaluate_tod_xyz`` with the directions given as longitude /
+        latitude [rad] (N,) of a frame whose constant rotation to the mean ecliptic is the 3x3
+        ``frame_rotation`` (``None``: ecliptic angles).  Additive entry: the
+        unit vectors of ``zodipy/model.py:247-251`` are formed and rotated in the kernel prologue,
+        so the host neither builds nor uploads the (3, N) array (16 instead of 24 B per line of
+        sight cross the bus)."""
+        return self.device_model.evaluate_lonlat(
+            lon, lat, obs_xyz, earth_xyz, rot=frame_rotation, return_comps=return_comps,
+            precision=precision or self._precision, out=out, out_dtype=out_dtype,
+            outside_flags=outside_flags, ephemeris=ephemeris, obstime=obstime, observer=observer)
+
     def evaluate_healpix(self, nside: int, obs_xyz, earth_xyz=None, *, frame_rotation=None,
                          pix_range=None, nest: bool = False, return_comps: bool = False,
                          precision: str | None = None, out=None, out_dtype=None, device_out: bool = False):
@@ -167,18 +187,28 @@ class Model:
 
         from . import astro  # lazy: needs astropy
 
+        # directions: angles + one 3x3 matrix for the device, or Astropy-transformed vectors
+        sky = astro.sky_lonlat_rotation(skycoord) if self._sky_rotation == "device" else None
         interp_obstimes = None
         if skycoord.obstime.size != 1:
             interp_obstimes = astro.arrange_obstimes(skycoord.obstime[0].mjd, skycoord.obstime[-1].mjd)
             if obspos_isstr and self._tod_ephemeris == "device" and interp_obstimes.size >= 4:
                 # hourly knots -> device splines; per-sample interpolation in the kernel prologue
-                eph, mode, u_xyz, mjd = astro.device_ephemeris(skycoord, obspos, interp_obstimes,
-                                                               self._ephemeris, self._device)
-                emission = self.evaluate_tod_xyz(u_xyz, mjd, eph, observer=mode, return_comps=return_comps)
+                eph, mode, u_xyz, mjd = astro.device_ephemeris(
+                    skycoord, obspos, interp_obstimes, self._ephemeris, self._device, with_directions=sky is None)
+                if sky is None:
+                    emission = self.evaluate_tod_xyz(u_xyz, mjd, eph, observer=mode, return_comps=return_comps)
+                else:
+                    emission = self.evaluate_lonlat(sky[0], sky[1], frame_rotation=sky[2], ephemeris=eph,
+                                                    obstime=mjd, observer=mode, return_comps=return_comps)
                 return astro.as_mjy_per_sr(emission)
         earth_xyz, obs_xyz, u_xyz = astro.prepare_arrays(
-            skycoord, obspos, obspos_isstr, interp_obstimes, self._ephemeris)
-        emission = self.evaluate_xyz(u_xyz, obs_xyz, earth_xyz, return_comps=return_comps)
+            skycoord, obspos, obspos_isstr, interp_obstimes, self._ephemeris, with_directions=sky is None)
+        if sky is None:
+            emission = self.evaluate_xyz(u_xyz, obs_xyz, earth_xyz, return_comps=return_comps)
+        else:
+            emission = self.evaluate_lonlat(sky[0], sky[1], obs_xyz, earth_xyz, frame_rotation=sky[2],
+                                            return_comps=return_comps)
         return astro.as_mjy_per_sr(emission)
 
     # ---------------------------------------------------------------------------------------
