@@ -100,7 +100,8 @@ def run(label, model, u, obs, earth, skip_fp64_above):
 def tod_e2e(dev, n=20_000_000):
     """Time-ordered data END TO END from pinned host memory: (a) the reference's array seam with
     per-sample observer/Earth arrays (72 B per sample up), (b) on-device ephemeris splines
-    (pointing + time, 32 B per sample up)."""
+    (pointing + time, 32 B per sample up), (c) the same with the pointing as longitude / latitude
+    (24 B per sample up; unit vectors formed in the kernel prologue)."""
     import time
 
     from scipy.interpolate import CubicSpline
@@ -120,6 +121,7 @@ def tod_e2e(dev, n=20_000_000):
     earth = CubicSpline(tk, earth_knots, axis=-1)(t)  # what the reference does per sample on the host
     host_interp_s = time.perf_counter() - tic
     earth, t_p = pin(earth), pin(t)
+    lon_p, lat_p = pin(np.arctan2(u[1], u[0])), pin(np.arcsin(np.clip(u[2], -1.0, 1.0)))
     out = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
     model = zp.Model(zp.Quantity(25.0, "um"), precision="fp32")
     eph = engine.DeviceEphemeris(t0, dt, earth_knots)
@@ -128,6 +130,8 @@ def tod_e2e(dev, n=20_000_000):
     variants = (
         ("array_seam_72B_per_sample", lambda: model.evaluate_xyz(u, earth, earth, out=out, out_dtype=np.float32)),
         ("device_ephemeris_32B_per_sample", lambda: model.evaluate_tod_xyz(u, t_p, eph, out=out, out_dtype=np.float32)),
+        ("device_ephemeris_lonlat_24B_per_sample",
+         lambda: model.evaluate_lonlat(lon_p, lat_p, ephemeris=eph, obstime=t_p, out=out, out_dtype=np.float32)),
         ("device_ephemeris_times_sent_twice_40B", lambda: model.evaluate_tod_xyz(u, t_p, eph, out=out, out_dtype=np.float32)))
     best = {label: float("inf") for label, _ in variants}
     sums = {}

@@ -1,9 +1,12 @@
 """Astropy-side host preparation for ``Model.evaluate`` (imported lazily; needs Astropy).
 
-Ephemerides and frame rotation stay on the Python host by design (BASELINE north star).  This
-follows ``zodipy/bodies.py:16-99`` and ``zodipy/model.py:212-251``: Earth / observer heliocentric
+Ephemerides stay on the Python host by design (BASELINE north star).  This follows
+``zodipy/bodies.py:16-99`` and ``zodipy/model.py:212-251``: Earth / observer heliocentric
 mean-ecliptic positions (hourly knots + cubic spline for time-ordered data, the SEMB-L2
-approximation) and rotation of the sky coordinates to ``BarycentricMeanEcliptic`` unit vectors.
+approximation) and the sky coordinates as ``BarycentricMeanEcliptic`` unit vectors - either
+transformed by Astropy on the host (``sky_unit_vectors``) or, when the frame differs from the mean
+ecliptic by a fixed rotation, handed to the device as angles + that rotation
+(``sky_lonlat_rotation``).
 """
 from __future__ import annotations
 

@@ -45,12 +45,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [find_nvcc(), *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    # compile next to the target and rename: a reader (another process, a gpurun snapshot) never
+    # sees a half-written library
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd += ["-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd))
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
