@@ -324,6 +324,38 @@ def test_evaluate_lonlat_equals_array_seam(name, x, unit, precision):
         model.evaluate_lonlat(lon, lat[:-1], EARTH_20220114)
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_multi_device_host_sharding_bitwise(precision):
+    """Model(devices=[...]) splits host arrays over several device handles driven by threads of one
+    process (here: all on GPU 0, or spread over the GPUs present); bit-identical to one handle,
+    including time-ordered data whose observers straddle a cutoff sphere (global early-out flags)."""
+    import torch
+
+    devices = [i % torch.cuda.device_count() for i in range(3)]
+    one = zp.Model(zp.Quantity(25.0, "um"), precision=precision, device=0)
+    many = zp.Model(zp.Quantity(25.0, "um"), precision=precision, devices=devices)
+    case, a = golden_case("dirbe_25um_tod_straddle")
+    ref = one.evaluate_xyz(a["u"], a["obs"], a["earth"], return_comps=True)
+    got = many.evaluate_xyz(a["u"], a["obs"], a["earth"], return_comps=True)
+    np.testing.assert_array_equal(got, ref)
+    rng = np.random.default_rng(2)
+    n = 1_500_001
+    lon, lat = rng.uniform(0, 2 * np.pi, n), np.arcsin(rng.uniform(-1, 1, n))
+    rot = _random_rotation(4)
+    ref = one.evaluate_lonlat(lon, lat, EARTH_20220114, frame_rotation=rot, out_dtype=np.float32)
+    got = many.evaluate_lonlat(lon, lat, EARTH_20220114, frame_rotation=rot, out_dtype=np.float32)
+    np.testing.assert_array_equal(got, ref)
+    u = rot @ _sph2cart(lon, lat)
+    np.testing.assert_array_equal(many.evaluate_xyz(u, EARTH_20220114), one.evaluate_xyz(u, EARTH_20220114))
+    # parameter updates reach every device
+    params = many.get_parameters()
+    params["comps"]["cloud"]["n_0"] *= 1.5
+    many.update_parameters(params)
+    one.update_parameters(params)
+    np.testing.assert_array_equal(many.evaluate_xyz(u[:, :5000], EARTH_20220114, return_comps=True),
+                                  one.evaluate_xyz(u[:, :5000], EARTH_20220114, return_comps=True))
+
+
 def test_evaluate_lonlat_with_device_ephemeris_and_multiband():
     n = 20000
     rng = np.random.default_rng(4)

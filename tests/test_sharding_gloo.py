@@ -103,3 +103,62 @@ def test_sharded_equals_single_rank_bitwise(world, case_id, per_sample):
     _, a = golden_case(case_id)
     for r in range(world):
         np.testing.assert_array_equal(results[r], a["emission"])  # every rank holds the full map
+
+
+@pytest.mark.parametrize("n_devices", [2, 3])
+@pytest.mark.parametrize("case_id,per_sample", [("dirbe_25um_tod_straddle", True), ("planck18_857", False)])
+def test_single_process_multi_device_host_sharding(monkeypatch, n_devices, case_id, per_sample):
+    """MultiDeviceModel (one process driving several GPUs for host arrays): array_split shards,
+    flags formed once from ALL observers, results written in place into one output - bit-identical to
+    the unsharded evaluation.  The per-device compute is stubbed by the oracle."""
+    from zodipy_b200 import engine
+
+    case, a = golden_case(case_id)
+    spec = case["spec"]
+    calls = []
+
+    class StubDeviceModel:
+        def __init__(self, spec_, device):
+            self.spec, self.device, self.ncomps = spec_, device, len(spec_["comps"])
+            self._eval = _oracle_with_flags(spec_)
+
+        def outside_flags(self, obs):
+            return spec_outside_flags(self.spec, float(np.sqrt((np.asarray(obs) ** 2).sum(axis=0)).max()))
+
+        def evaluate(self, u, obs, earth, *, return_comps, precision, out, out_dtype, outside_flags):
+            calls.append((self.device, u.shape[1], obs.shape[1]))
+            assert out.strides[-1] == out.itemsize and out.dtype == out_dtype
+            out[...] = self._eval(u, obs, earth, outside_flags, return_comps).numpy()
+
+        def evaluate_lonlat(self, lon, lat, obs, earth, *, rot, **kw):
+            u = np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+            self.evaluate(u if rot is None else np.asarray(rot).reshape(3, 3) @ u, obs, earth, **kw)
+
+        def update(self, spec_):
+            self.spec = spec_
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(engine, "DeviceModel", StubDeviceModel)
+    multi = engine.MultiDeviceModel(spec, list(range(n_devices)))
+    n = a["u"].shape[1]
+    got = multi.evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
+    np.testing.assert_array_equal(got, a["emission"])
+    assert sorted(c[1] for c in calls) == sorted(hi - lo for lo, hi in sharding.split_bounds(n, n_devices))
+    assert all(c[2] == (c[1] if per_sample else 1) for c in calls)
+    out = np.full(n, np.nan)
+    assert multi.evaluate(a["u"], a["obs"], a["earth"], out=out) is out
+    np.testing.assert_array_equal(out, a["emission"].sum(axis=0))
+    # spherical-coordinate entry: same shards, angles split instead of vectors
+    lon, lat = np.arctan2(a["u"][1], a["u"][0]), np.arcsin(np.clip(a["u"][2], -1, 1))
+    got_ll = multi.evaluate_lonlat(lon, lat, a["obs"], a["earth"], return_comps=True)
+    np.testing.assert_allclose(got_ll, a["emission"], rtol=1e-9, atol=1e-30)
+    # fewer lines of sight than devices: empty shards are skipped
+    few = multi.evaluate(a["u"][:, :1], a["obs"][:, :1], a["earth"][:, :1])
+    assert few.shape == (1,) and np.isfinite(few).all()
+    assert multi.evaluate(np.empty((3, 0)), a["obs"][:, :1]).shape == (0,)
+    with pytest.raises(ValueError):
+        multi.evaluate(a["u"], a["obs"][:, :2] if per_sample else np.ones((3, 2)))
+    with pytest.raises(ValueError):
+        engine.MultiDeviceModel(spec, [])

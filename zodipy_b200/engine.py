@@ -310,9 +310,11 @@ class DeviceModel:
         else:
             if out is None:
                 out = np.empty(shape, dtype=out_dtype)
-            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
-                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            elif out.shape != shape or out.dtype != out_dtype or out.strides[-1] != out.itemsize:
+                # rows may be strided (a column block of a larger (ncomps, N) array: one shard's output)
+                raise ValueError("out has wrong shape/dtype or its last axis is not contiguous")
             out_ptr = out.ctypes.data
+            out_row_stride = out.strides[0] // out.itemsize if out.ndim == 2 and n > 1 else n
             stream = None
         if n == 0:
             return out
@@ -341,7 +343,7 @@ class DeviceModel:
         args.precision = _PRECISIONS[precision]
         args.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
         args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
-        args.out, args.out_stride = out_ptr, n
+        args.out, args.out_stride = out_ptr, (n if device_mem or peer_map is not None else out_row_stride)
         args.stream = stream
         if peer_map is not None:
             args.n_peers = len(peer_map.pointers)
@@ -535,6 +537,96 @@ class DeviceModel:
 
     def last_kernel_ms(self) -> float:
         return float(self._lib.zodi_last_kernel_ms(self._handle))
+
+
+class MultiDeviceModel:
+    """One model replicated on several GPUs of the box, driven from ONE process for host arrays.
+
+    The GPU counterpart of the reference's ``nprocesses`` fork pool (``zodipy/model.py:182-198``) for a
+    caller that is not launched with one process per GPU: the lines of sight are split into
+    ``np.array_split`` chunks (per-sample observer / Earth arrays likewise, single positions and the
+    parameters replicated), every chunk is integrated by its own device through the library's pipelined
+    host path (each GPU moves its chunk over its own PCIe link), and the results land in place in the
+    one output array - the ``np.concatenate`` of the reference without a copy.  The early-out flags are
+    formed once from ALL observers (quirk Q1), so the result is bit-identical to a single-device call.
+    ctypes releases the GIL during the calls, so plain Python threads keep all devices busy.
+    """
+
+    def __init__(self, spec: dict, devices):
+        devices = [int(d) for d in devices]
+        if not devices:
+            raise ValueError("devices must not be empty")
+        self.devices = devices
+        self.models = [DeviceModel(spec, d) for d in devices]
+        self.spec = spec
+        self.ncomps = self.models[0].ncomps
+
+    def update(self, spec: dict) -> None:
+        for m in self.models:
+            m.update(spec)
+        self.spec = spec
+        self.ncomps = self.models[0].ncomps
+
+    def close(self) -> None:
+        for m in self.models:
+            m.close()
+
+    def _run(self, n, obs, earth, return_comps, out, out_dtype, outside_flags, call):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .sharding import split_bounds
+
+        out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        shape = (self.ncomps, n) if return_comps else (n,)
+        if out is None:
+            out = np.empty(shape, dtype=out_dtype)
+        elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+            raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+        if n == 0:
+            return out
+        obs = np.asarray(obs, dtype=np.float64).reshape(3, -1)
+        earth = obs if earth is None else np.asarray(earth, dtype=np.float64).reshape(3, -1)
+        if obs.shape[1] not in (1, n) or earth.shape[1] not in (1, n):
+            raise ValueError("obs/earth must hold one position or one per line of sight")
+        flags = self.models[0].outside_flags(obs) if outside_flags is None else outside_flags
+        shards = [(m, lo, hi) for m, (lo, hi) in zip(self.models, split_bounds(n, len(self.models))) if hi > lo]
+
+        def work(item):
+            m, lo, hi = item
+            part = lambda a: a[:, lo:hi] if a.shape[1] == n and n > 1 else a  # noqa: E731
+            call(m, lo, hi, part(obs), part(earth), out[..., lo:hi], flags)
+
+        with ThreadPoolExecutor(max_workers=len(shards)) as pool:
+            list(pool.map(work, shards))  # re-raises the first worker exception
+        return out
+
+    def evaluate(self, u, obs, earth=None, *, return_comps: bool = False, precision: str = "fp64", out=None,
+                 out_dtype=None, outside_flags=None):
+        """Like :meth:`DeviceModel.evaluate` for NumPy inputs, sharded over ``devices``."""
+        u = np.asarray(u, dtype=np.float64)
+        if u.ndim != 2 or u.shape[0] != 3:
+            raise ValueError("unit_vectors must have shape (3, n)")
+        n = u.shape[1]
+
+        def call(m, lo, hi, o, e, out_part, flags):
+            m.evaluate(u[:, lo:hi], o, e, return_comps=return_comps, precision=precision, out=out_part,
+                       out_dtype=out_part.dtype, outside_flags=flags)
+
+        return self._run(n, obs, earth, return_comps, out, out_dtype, outside_flags, call)
+
+    def evaluate_lonlat(self, lon, lat, obs, earth=None, *, rot=None, return_comps: bool = False,
+                        precision: str = "fp64", out=None, out_dtype=None, outside_flags=None):
+        """Like :meth:`DeviceModel.evaluate_lonlat` for NumPy inputs, sharded over ``devices``."""
+        lon = np.ascontiguousarray(lon, dtype=np.float64).reshape(-1)
+        lat = np.ascontiguousarray(lat, dtype=np.float64).reshape(-1)
+        if lon.size != lat.size:
+            raise ValueError("lon and lat must have the same length")
+
+        def call(m, lo, hi, o, e, out_part, flags):
+            m.evaluate_lonlat(lon[lo:hi], lat[lo:hi], o, e, rot=rot, return_comps=return_comps, precision=precision,
+                              out=out_part, out_dtype=out_part.dtype, outside_flags=flags)
+
+        return self._run(lon.size, obs, earth, return_comps, out, out_dtype, outside_flags, call)
 
 
 class DeviceMultiBand(DeviceModel):

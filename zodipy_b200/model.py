@@ -36,7 +36,7 @@ class Model:
     def __init__(self, x, *, weights=None, name: str = "dirbe", gauss_quad_degree: int = 50,
                  extrapolate: bool = False, ephemeris: str = "builtin",
                  precision: str = "fp64", device: int | None = None,
-                 tod_ephemeris: str = "host", sky_rotation: str = "device") -> None:
+                 tod_ephemeris: str = "host", sky_rotation: str = "device", devices=None) -> None:
         try:
             if not x.isscalar and weights is None:
                 raise ValueError("Bandpass weights must be provided for non-scalar `x`.")
@@ -76,8 +76,15 @@ class Model:
         self._gauss_quad_degree = int(gauss_quad_degree)
         self._ephemeris = ephemeris
         self._precision = precision
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            if not devices or (device is not None and int(device) != devices[0]):
+                raise ValueError("devices must be a non-empty list whose first entry equals device (if given)")
+            device = devices[0]
         self._device = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
+        self._devices = devices if devices is not None else [self._device]
         self._device_model: DeviceModel | None = None
+        self._multi_model = None
         self._init_ipd_model_partials()
 
     # ---------------------------------------------------------------------------------------
@@ -88,6 +95,8 @@ class Model:
         self._b_nu_table = self._spec["table"]
         if self._device_model is not None:
             self._device_model.update(self._spec)
+        if self._multi_model is not None:
+            self._multi_model.update(self._spec)
 
     @property
     def spec(self) -> dict:
@@ -104,6 +113,16 @@ class Model:
             self._device_model = DeviceModel(self._spec, self._device)
         return self._device_model
 
+    def _multi(self, *arrays):
+        """The multi-GPU engine when ``devices`` names several GPUs and the inputs are host arrays."""
+        if len(self._devices) < 2 or any(type(a).__module__.startswith("torch") for a in arrays):
+            return None
+        if self._multi_model is None:
+            from .engine import MultiDeviceModel
+
+            self._multi_model = MultiDeviceModel(self._spec, self._devices)
+        return self._multi_model
+
     # ---------------------------------------------------------------------------------------
     def evaluate_xyz(self, unit_vectors, obs_xyz, earth_xyz=None, *, return_comps: bool = False,
                      precision: str | None = None, out=None, out_dtype=None, outside_flags=None):
@@ -113,6 +132,11 @@ class Model:
         heliocentric ecliptic positions [AU] (``earth_xyz`` defaults to ``obs_xyz``).  NumPy in ->
         NumPy out; torch CUDA tensors in -> torch CUDA tensor out.  Values are MJy/sr.
         """
+        multi = self._multi(unit_vectors)
+        if multi is not None:
+            return multi.evaluate(unit_vectors, obs_xyz, earth_xyz, return_comps=return_comps,
+                                  precision=precision or self._precision, out=out, out_dtype=out_dtype,
+                                  outside_flags=outside_flags)
         return self.device_model.evaluate(
             unit_vectors, obs_xyz, earth_xyz, return_comps=return_comps,
             precision=precision or self._precision, out=out, out_dtype=out_dtype,
@@ -143,6 +167,11 @@ class Model:
         unit vectors of ``zodipy/model.py:247-251`` are formed and rotated in the kernel prologue,
         so the host neither builds nor uploads the (3, N) array (16 instead of 24 B per line of
         sight cross the bus)."""
+        multi = self._multi(lon, lat) if ephemeris is None else None
+        if multi is not None:
+            return multi.evaluate_lonlat(lon, lat, obs_xyz, earth_xyz, rot=frame_rotation, return_comps=return_comps,
+                                         precision=precision or self._precision, out=out, out_dtype=out_dtype,
+                                         outside_flags=outside_flags)
         return self.device_model.evaluate_lonlat(
             lon, lat, obs_xyz, earth_xyz, rot=frame_rotation, return_comps=return_comps,
             precision=precision or self._precision, out=out, out_dtype=out_dtype,
