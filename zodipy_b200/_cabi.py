@@ -26,7 +26,8 @@ MEM_HOST, MEM_DEVICE = 0, 1
 PEAK_FP32_FMA, PEAK_FP64_FMA, PEAK_MUFU_EX2, PEAK_HBM_COPY = 0, 1, 2, 3
 
 LIB_NAME = "libzodi_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# ZODI_B200_LIB: load another build of the same library (A/B measurements of kernel variants only)
+LIB_PATH = os.environ.get("ZODI_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 c_double_p = C.POINTER(C.c_double)
 c_uint8_p = C.POINTER(C.c_uint8)

@@ -15,7 +15,13 @@
 
 #include "zodi_kelsall.cuh"
 
+#ifndef ZODI_X2_UNROLL
+#define ZODI_X2_UNROLL 1  // node-loop unroll factor of the packed cloud + bands loop (measured: see DESIGN.md)
+#endif
+
 namespace zodi {
+
+constexpr int kX2Unroll = ZODI_X2_UNROLL;
 
 struct alignas(8) F2 { float x, y; };
 
@@ -93,22 +99,49 @@ ZODI_HD F2 scatter_term2(const KelsallModel<float>& K, F2 ux, F2 uy, F2 uz, F2 x
     return mul2(mul2(phase_of_cos2(K, ct), rh_inv), rh_inv);
 }
 
+// Loop-invariant handle of the staged table for table_at2.  Device: the shared-window byte address of
+// the table minus 8 * 0x4B400000 (mod 2^32), so that entry i is at handle + 8 * bits(s) with s = magic + i
+// and the index extraction costs one shift-add per lookup; the value passes through a warp shuffle
+// (once per line of sight), otherwise ptxas re-associates the constant back into the loop (one more add
+// per lookup).
+struct TableRef {
+#if defined(__CUDA_ARCH__)
+    uint32_t base;
+#else
+    const Pair<float>* tab;
+#endif
+};
+ZODI_HD TableRef table_ref(const Pair<float>* tab) {
+    TableRef r;
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(tab) - (0x4B400000u << 3);
+    r.base = __shfl_sync(0xffffffffu, b, 0);  // opaque to ptxas, unlike a move
+#else
+    r.tab = tab;
+#endif
+    return r;
+}
+
 // Table lookup for two temperatures (same arithmetic as table_at<float>).
-ZODI_HD F2 table_at2(const Pair<float>* tab, F2 t, float t_top) {
+ZODI_HD F2 table_at2(TableRef ref, F2 t, float t_top) {
     t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
     const float magic = 12582912.0f;
     const F2 s = add2(add2(t, -0.5f), magic);
+    Pair<float> e0, e1;
 #if defined(__CUDA_ARCH__)
-    const int i0 = __float_as_int(s.x) - 0x4B400000, i1 = __float_as_int(s.y) - 0x4B400000;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e0.a), "=f"(e0.b) : "r"(ref.base + (__float_as_uint(s.x) << 3)));
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e1.a), "=f"(e1.b) : "r"(ref.base + (__float_as_uint(s.y) << 3)));
 #else
     int b0, b1;
     memcpy(&b0, &s.x, 4);
     memcpy(&b1, &s.y, 4);
-    const int i0 = b0 - 0x4B400000, i1 = b1 - 0x4B400000;
+    e0 = ref.tab[b0 - 0x4B400000];
+    e1 = ref.tab[b1 - 0x4B400000];
 #endif
-    const Pair<float> e0 = tab[i0], e1 = tab[i1];
     const F2 frac = fma2(add2(s, -magic), -1.0f, t);  // t - (s - magic)
-    return fma2(f2(e0.b, e1.b), frac, f2(e0.a, e1.a));
+    // two scalar FMAs: the table entries arrive as (a, b) pairs per half, so a packed FMA would need
+    // four register moves to regroup them into (b0, b1) / (a0, a1) (3 issue slots more; same FMA-pipe load)
+    return f2(fmaf(e0.b, frac.x, e0.a), fmaf(e1.b, frac.y, e1.a));
 }
 
 // 1 - 2^-y for both halves (same switch and polynomial as Math<float>::one_minus_exp2_neg); the
@@ -125,14 +158,17 @@ ZODI_HD F2 one_minus_exp2_neg2(F2 y) {
 // (R > 1.15 delta_r, most of a line of sight that runs out to 5.2 AU) 2^(-y^10) < 2^-25 and the term
 // rounds to exactly 1: when the whole warp is there the power chain, the polynomial and the MUFU pair
 // are skipped.
-ZODI_HD F2 band_radial2(F2 Rh2, float by) {
+// rr = rinv * (1 - 2^(-y^10)) and true, or false when the term is skipped for the whole warp: the factor is
+// then rinv itself (x * 1 == x exactly) and the caller passes rinv on, so neither the constant 1, the
+// product nor a register copy is formed.
+ZODI_HD bool band_radial2(F2 Rh2, float by, F2 rinv, F2& rr) {
     const F2 y = mul2(Rh2, by);
-    F2 rad = f2(1.0f);
-    if (warp_any(y.x < Math<float>::kRadialOne || y.y < Math<float>::kRadialOne)) {
+    const bool cut = warp_any(y.x < Math<float>::kRadialOne || y.y < Math<float>::kRadialOne);  // warp-uniform
+    if (cut) {
         const F2 y2 = mul2(y, y), y4 = mul2(y2, y2), y5 = mul2(y4, y);
-        rad = one_minus_exp2_neg2(mul2(y5, y5));
+        rr = mul2(rinv, one_minus_exp2_neg2(mul2(y5, y5)));
     }
-    return rad;
+    return cut;
 }
 
 // Adds w*B * n_band to acc, n_band = exp(-s^6) (1 + s^4/v) * (rinv * rad); skipped (n_band == 0)
@@ -162,6 +198,10 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     const F2 ox = f2(Ga.ox, Gb.ox), oy = f2(Ga.oy, Gb.oy), oz = f2(Ga.oz, Gb.oz);
     F2 a0 = f2(0.f), a1 = f2(0.f), a2 = f2(0.f), a3 = f2(0.f);
     F2 s0 = f2(0.f), s1 = f2(0.f), s2 = f2(0.f), s3 = f2(0.f);  // scattering accumulators
+    const TableRef tref = table_ref(tab);
+#if defined(__CUDA_ARCH__)
+#pragma unroll kX2Unroll
+#endif
     for (int k = 0; k < K.n_nodes; ++k) {
         const Pair<float> nw = nodes[k];
         // shared source quantities (node_source<float, false>)
@@ -170,18 +210,31 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
         const F2 lgR = lg2_2(Rh2);
         const F2 t = fma2(ex2_2(mul2(lgR, K.mhd)), K.t_scale, K.t_ofs);
-        const F2 B = table_at2(tab, t, K.t_top);
+        const F2 B = table_at2(tref, t, K.t_top);
         // bands
         const F2 rinv = rsq_2(Rh2);
-        const F2 rad1 = band_radial2(Rh2, K.b_y[0]);
-        const F2 rad2 = band_radial2(Rh2, K.b_y[1]);
-        const F2 rad3 = SHARE13 ? rad1 : band_radial2(Rh2, K.b_y[2]);
         const F2 wB = mul2(B, nw.b);
         F2 wF = f2(0.f);
         if (SCATTER) wF = mul2(scatter_term2(K, ux, uy, uz, xh, yh, zh, rinv), nw.b);  // rinv == 1/R_h (bands are Sun-centred)
-        band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad1), K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
-        band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad2), K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
-        band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, mul2(rinv, rad3), K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        F2 rr = rinv;
+        // the two sides of each branch are the same calls with rr or rinv as the radial factor
+        if (band_radial2(Rh2, K.b_y[0], rinv, rr)) {
+            band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rr, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+            if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        } else {
+            band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+            if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        }
+        if (band_radial2(Rh2, K.b_y[1], rinv, rr))
+            band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rr, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+        else
+            band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+        if (!SHARE13) {
+            if (band_radial2(Rh2, K.b_y[2], rinv, rr))
+                band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+            else
+                band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        }
         // cloud
         const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
         const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
@@ -218,13 +271,14 @@ ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pai
     const F2 R0 = f2(-K.r_R, -K.f_R), c2 = f2(K.r_c2, K.f_c2), c3 = f2(K.r_c3, K.f_c3);
     const F2 nx = f2(K.rnx, K.fnx), ny = f2(K.rny, K.fny), nz = f2(K.rnz, K.fnz);
     F2 acc = f2(0.f), accS = f2(0.f);
+    const TableRef tref = table_ref(tab);
     for (int k = 0; k < K.n_nodes; ++k) {
         const Pair<float> nw = nodes[k];
         const F2 R_los = fma2(h, nw.a, mid);
         const F2 xh = fma2(R_los, G.ux, G.ox), yh = fma2(R_los, G.uy, G.oy), zh = fma2(R_los, G.uz, G.oz);
         const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
         const F2 t = fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs);
-        const F2 B = table_at2(tab, t, K.t_top);
+        const F2 B = table_at2(tref, t, K.t_top);
         const F2 d = add2(sqrt_2(Rh2), R0);
         const F2 Zc = fma2(xh, nx, fma2(yh, ny, mul2(zh, nz)));
         const float xr = fmaf(xh.y, cr, yh.y * sr), yr = fmaf(yh.y, cr, -(xh.y * sr));
