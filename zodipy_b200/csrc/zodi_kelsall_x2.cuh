@@ -177,8 +177,11 @@ template <bool SCATTER>
 ZODI_HD void band_accumulate2(F2& acc, F2& accS, F2 wB, F2 wF, F2 xh, F2 yh, F2 zh, F2 rinv, F2 rinv_rad,
                               float bx, float by, float bz, float c3) {
     const F2 sz = mul2(fma2(xh, bx, fma2(yh, by, mul2(zh, bz))), rinv);
-    const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2), s6 = mul2(s4, s2);
-    if (warp_any(s6.x <= Math<float>::kEx2Underflow || s6.y <= Math<float>::kEx2Underflow)) {
+    const F2 s2 = mul2(sz, sz);
+    // a warp whose lanes all have s^2 > kS2Underflow has exp(-s^6) == 0 in every lane (the scalar kernel
+    // tests s^6 <= 126; lanes between the two thresholds get an exact 0 from the flushed ex2 instead)
+    if (warp_any(s2.x <= Math<float>::kS2Underflow || s2.y <= Math<float>::kS2Underflow)) {
+        const F2 s4 = mul2(s2, s2), s6 = mul2(s4, s2);
         const F2 n = mul2(mul2(ex2_neg2(s6), fma2(s4, c3, 1.0f)), rinv_rad);
         acc = fma2(wB, n, acc);
         if (SCATTER) accS = fma2(wF, n, accS);
@@ -199,6 +202,7 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     F2 a0 = f2(0.f), a1 = f2(0.f), a2 = f2(0.f), a3 = f2(0.f);
     F2 s0 = f2(0.f), s1 = f2(0.f), s2 = f2(0.f), s3 = f2(0.f);  // scattering accumulators
     const TableRef tref = table_ref(tab);
+    const float by_min = fminf(K.b_y[0], fminf(K.b_y[1], K.b_y[2]));
 #if defined(__CUDA_ARCH__)
 #pragma unroll kX2Unroll
 #endif
@@ -216,24 +220,33 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 wB = mul2(B, nw.b);
         F2 wF = f2(0.f);
         if (SCATTER) wF = mul2(scatter_term2(K, ux, uy, uz, xh, yh, zh, rinv), nw.b);  // rinv == 1/R_h (bands are Sun-centred)
+        // 1 - 2^(-y^10) is exactly 1 for every band once R^2 * min(b_y) >= kRadialOne in all lanes (b_y > 0:
+        // the products are monotonic in b_y): one test then replaces the per-band ones - the common case
         F2 rr = rinv;
-        // the two sides of each branch are the same calls with rr or rinv as the radial factor
-        if (band_radial2(Rh2, K.b_y[0], rinv, rr)) {
-            band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rr, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
-            if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
-        } else {
+        const F2 ymin = mul2(Rh2, by_min);
+        if (!warp_any(ymin.x < Math<float>::kRadialOne || ymin.y < Math<float>::kRadialOne)) {
             band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
-            if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
-        }
-        if (band_radial2(Rh2, K.b_y[1], rinv, rr))
-            band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rr, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
-        else
             band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
-        if (!SHARE13) {
-            if (band_radial2(Rh2, K.b_y[2], rinv, rr))
-                band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+            band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        } else {
+            // the two sides of each branch are the same calls with rr or rinv as the radial factor
+            if (band_radial2(Rh2, K.b_y[0], rinv, rr)) {
+                band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rr, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+                if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+            } else {
+                band_accumulate2<SCATTER>(a1, s1, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+                if (SHARE13) band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+            }
+            if (band_radial2(Rh2, K.b_y[1], rinv, rr))
+                band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rr, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
             else
-                band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+                band_accumulate2<SCATTER>(a2, s2, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+            if (!SHARE13) {
+                if (band_radial2(Rh2, K.b_y[2], rinv, rr))
+                    band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rr, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+                else
+                    band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+            }
         }
         // cloud
         const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
