@@ -273,10 +273,18 @@ template <bool HAS_RF, bool SHARE13, bool SCATTER>
 cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
                               const Pair<float>* nodes, cudaStream_t stream) {
     const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
-    // cloud+bands only: 5 CTAs/SM (48 registers) measured 5 % faster than 4 CTAs/SM (60 registers)
-    // on B200; the ring/feature loops and the scattering terms need more registers (4 / 3 CTAs/SM; 4 CTAs/SM
-    // with scattering measured equal to 3).
-    constexpr int kMinCtas = SCATTER ? 3 : (HAS_RF ? 4 : 5);
+    // 5 CTAs/SM (48 registers): cloud+bands only measured 5 % faster than 4 CTAs/SM (60 registers) and
+    // 0.4 % faster than 6 (40 registers); with the ring/feature loops 5 CTAs/SM is 0.8 % faster than 4 (64
+    // registers) - the spills it causes sit in the per-line-of-sight prologue / epilogue, not in the node
+    // loops.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  The macros exist for
+    // A/B builds (benchmarks/ab_kernel.py).
+#ifndef ZODI_X2_CTAS_THERMAL
+#define ZODI_X2_CTAS_THERMAL 5
+#endif
+#ifndef ZODI_X2_CTAS_RF
+#define ZODI_X2_CTAS_RF 5
+#endif
+    constexpr int kMinCtas = SCATTER ? 3 : (HAS_RF ? ZODI_X2_CTAS_RF : ZODI_X2_CTAS_THERMAL);
     zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, kMinCtas>
         <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
     g_launches.fetch_add(1);

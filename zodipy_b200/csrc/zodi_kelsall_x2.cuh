@@ -215,6 +215,16 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 lgR = lg2_2(Rh2);
         const F2 t = fma2(ex2_2(mul2(lgR, K.mhd)), K.t_scale, K.t_ofs);
         const F2 B = table_at2(tref, t, K.t_top);
+        // cloud: independent of the bands, placed next to the source terms so that its chain of ten MUFU ops
+        // overlaps their arithmetic (the band blocks below are separated by warp votes, which fence scheduling)
+        const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
+        const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
+        const F2 Zc = fma2(xc, K.cnx, fma2(yc, K.cny, mul2(zc, K.cnz)));
+        const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
+        const F2 g_in = mul2(mul2(zeta, zeta), K.c_inv2mu), g_out = add2(zeta, -K.c_halfmu);
+        const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
+        const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
+        const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
         // bands
         const F2 rinv = rsq_2(Rh2);
         const F2 wB = mul2(B, nw.b);
@@ -248,15 +258,6 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
                     band_accumulate2<SCATTER>(a3, s3, wB, wF, xh, yh, zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
             }
         }
-        // cloud
-        const F2 xc = add2(xh, -K.cx0), yc = add2(yh, -K.cy0), zc = add2(zh, -K.cz0);
-        const F2 Rc2 = fma2(xc, xc, fma2(yc, yc, mul2(zc, zc)));
-        const F2 Zc = fma2(xc, K.cnx, fma2(yc, K.cny, mul2(zc, K.cnz)));
-        const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
-        const F2 g_in = mul2(mul2(zeta, zeta), K.c_inv2mu), g_out = add2(zeta, -K.c_halfmu);
-        const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
-        const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
-        const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
         a0 = fma2(wB, n0, a0);
         if (SCATTER) s0 = fma2(wF, n0, s0);
     }
