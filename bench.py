@@ -36,10 +36,11 @@ MODEL_NAME, X_GHZ, DEG = "planck18", 857.0, 50
 FLOPS_PER_UNIT = 60.25  # canonical algorithmic flops, Planck-type 4-comp mean
 SFU_PER_UNIT = 7.0
 # EXECUTED work of the packed fused kernel per evaluation, from the ncu capture committed as
-# profiles/r1_ncu_kelsall_x2_fp32_nside1024.md (per pair of lines of sight and node, / 8 evaluations):
-EXEC_ISSUE_PER_UNIT = 155.4 / 8   # warp-instruction issue slots
-EXEC_MUFU_PER_UNIT = 20.6 / 8     # XU-pipe instructions
-EXEC_FMA_CYCLES_PER_UNIT = 2 * 80.5 / 8  # FMA-pipe cycles (packed FFMA2/FMUL2/FADD2 take 2)
+# profiles/r1b_ncu_x2_planck18_nside2048.md (per pair of lines of sight and node, / 8 evaluations;
+# prologue included): 6.042e9 warp instructions, XU pipe 81.3 % and FMA pipe 63.3 % of 13.74e6 cycles.
+EXEC_ISSUE_PER_UNIT = 153.7 / 8   # warp-instruction issue slots
+EXEC_MUFU_PER_UNIT = 21.0 / 8     # XU-pipe instructions (8 cycles each per SM sub-partition)
+EXEC_FMA_CYCLES_PER_UNIT = 130.9 / 8  # FMA-pipe cycles (packed FFMA2/FMUL2/FADD2 take 2)
 # Same for the fp64 kernel, profiles/r1_ncu_fp64_planck18_nside1024.md: 80.3 thread-instructions per
 # evaluation of which 43.5 % go to the FP64 pipe (one warp instruction per two issue cycles).
 EXEC64_ISSUE_PER_UNIT = 80.3
@@ -468,7 +469,7 @@ def run_b200(args):
             "issue_slot_util": kernel_units_per_s * EXEC_ISSUE_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
             "xu_pipe_util": kernel_units_per_s * EXEC_MUFU_PER_UNIT / peak_mufu,
             "fma_pipe_util": kernel_units_per_s * EXEC_FMA_CYCLES_PER_UNIT / 32 / (sm_count * 4 * sm_hz),
-            "counts_from": "profiles/r1_ncu_kelsall_x2_fp32_nside1024.md"},
+            "counts_from": "profiles/r1b_ncu_x2_planck18_nside2048.md"},
         "algorithmic_hbm_bytes_per_los": 24 + (4 if precision == "fp32" else 8),
         "note": "compute-pipe bound (HBM traffic is 28-32 B per 200 evaluations); `peak` is the measured "
                 "pipe peak of the precision mode, not HBM/tensor",

@@ -54,6 +54,7 @@ struct KelsallModel {
     Real fnx, fny, fnz, f_R, f_c2, f_c3, f_c5, f_theta0;
     // ranges (always double)
     double cutA_in, cutA_out, cutR_in, cutR_out, cutF_in, cutF_out;
+    double f_cos0, f_sin0;  // cos / sin of the feature's theta_0 (see feature_rotation)
 };
 
 // --- table lookup -----------------------------------------------------------------------------
@@ -219,6 +220,23 @@ ZODI_HD Real kelsall_ring(const KelsallModel<Real>& K, const Pair<Real>* tab, co
     return h * M::fma_(K.aB[4], aB, K.aS[4] * aS);
 }
 
+// cos / sin of  theta = atan2(dey, dex) + theta_0  (Earth's longitude about the feature's centre plus
+// the trailing offset, number_density.py:163-170): the nodes are rotated by -theta so that atan2 returns
+// the wrapped longitude offset directly.  cos(atan2(y, x)) = x / r and sin = y / r, so the angle sum
+// needs one reciprocal square root instead of atan2 + cos + sin in double per line of sight.
+template <typename Real>
+ZODI_HD void feature_rotation(double dex, double dey, double cos0, double sin0, Real& cr, Real& sr) {
+    const double r2 = dex * dex + dey * dey;
+    double c = 1.0, s = 0.0;  // atan2(0, 0) = 0
+    if (r2 > 0.0) {
+        const double inv = Math<double>::rsqrt_(r2);
+        c = dex * inv;
+        s = dey * inv;
+    }
+    cr = Real(c * cos0 - s * sin0);
+    sr = Real(s * cos0 + c * sin0);
+}
+
 // ---------------- feature (own grid) ----------------------------------------------------------
 template <typename Real, bool SCATTER>
 ZODI_HD Real kelsall_feature(const KelsallModel<Real>& K, const Pair<Real>* tab, const Pair<Real>* nodes,
@@ -230,8 +248,8 @@ ZODI_HD Real kelsall_feature(const KelsallModel<Real>& K, const Pair<Real>* tab,
     // rotate by -(theta_earth + theta_0): then atan2 gives the wrapped longitude offset directly
     // (number_density.py:163-170; [-pi,pi) vs (-pi,pi] only differs at |delta| = pi where the
     // squared offset is identical)
-    const double th = atan2(dey, dex) + (double)K.f_theta0;
-    const Real cr = Real(cos(th)), sr = Real(sin(th));
+    Real cr, sr;
+    feature_rotation<Real>(dex, dey, K.f_cos0, K.f_sin0, cr, sr);
     Real aB = 0, aS = 0;
     for (int k = sub; k < K.n_nodes; k += L) {
         const Pair<Real> nw = nodes[k];

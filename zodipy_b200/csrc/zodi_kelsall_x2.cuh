@@ -280,8 +280,8 @@ ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pai
     los_interval<float>(G, K.cutR_in, K.cutR_out, (outside_mask >> 8) & 1u, (outside_mask >> 9) & 1u, hr, midr);
     los_interval<float>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, hf, midf);
     const F2 h = f2(hr, hf), mid = f2(midr, midf);
-    const double th = atan2(dey, dex) + (double)K.f_theta0;  // see kelsall_feature()
-    const float cr = float(cos(th)), sr = float(sin(th));
+    float cr, sr;
+    feature_rotation<float>(dex, dey, K.f_cos0, K.f_sin0, cr, sr);  // see kelsall_feature()
     const F2 R0 = f2(-K.r_R, -K.f_R), c2 = f2(K.r_c2, K.f_c2), c3 = f2(K.r_c3, K.f_c3);
     const F2 nx = f2(K.rnx, K.fnx), ny = f2(K.rny, K.fny), nz = f2(K.rnz, K.fnz);
     F2 acc = f2(0.f), accS = f2(0.f);

@@ -250,6 +250,7 @@ inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& 
         K.fnx = f.sin_Omega * f.sin_i; K.fny = -f.cos_Omega * f.sin_i; K.fnz = f.cos_i;
         K.f_R = f.shape[1]; K.f_c2 = -kLog2e / (f.shape[2] * f.shape[2]); K.f_c3 = -kLog2e / f.shape[3];
         K.f_theta0 = f.shape[4]; K.f_c5 = -kLog2e / (f.shape[5] * f.shape[5]);
+        K.f_cos0 = std::cos(f.shape[4]); K.f_sin0 = std::sin(f.shape[4]);
         K.cutF_in = f.cutoff_inner; K.cutF_out = f.cutoff_outer;
     }
     return true;
@@ -273,6 +274,7 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
 #undef ZN
     b.cutA_in = a.cutA_in; b.cutA_out = a.cutA_out; b.cutR_in = a.cutR_in; b.cutR_out = a.cutR_out;
     b.cutF_in = a.cutF_in; b.cutF_out = a.cutF_out;
+    b.f_cos0 = a.f_cos0; b.f_sin0 = a.f_sin0;
 }
 
 // Not-a-knot cubic spline through uniformly or non-uniformly spaced knots, one axis: the same

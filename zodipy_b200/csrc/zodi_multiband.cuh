@@ -178,8 +178,8 @@ ZODI_HD void integrate_kelsall_multiband(const MultiBandModel<Real>& MB, const P
         {
             Real h, mid;
             los_interval<Real>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, h, mid);
-            const double th = atan2(dey, dex) + (double)K.f_theta0;
-            const Real cr = Real(cos(th)), sr = Real(sin(th));
+            Real cr, sr;
+            feature_rotation<Real>(dex, dey, K.f_cos0, K.f_sin0, cr, sr);
             Real acc[NB];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
