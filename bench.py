@@ -104,6 +104,17 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout_s):
+        """nvidia-smi needs a moment to start: return once its first line is in the file."""
+        t_end = time.time() + timeout_s
+        while self.proc is not None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -297,15 +308,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled (nvidia-smi, 100 ms period) from before the warm-up until
+    # ~0.4 s of the same launches after the timed steps: the timed region itself lasts only tens of ms
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample(3.0)
     for _ in range(max(args.warmup, 3)):
         full = step()
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     launches0 = engine.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -349,8 +362,11 @@ def run_b200(args):
         t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, kernel_ms = float(t[0]), float(t[1])
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = elapsed_ms / args.steps
+    for _ in range(int(np.ceil(400.0 / max(ms_per_step, 1e-3)))):  # same count on every rank (elapsed_ms is reduced)
+        step()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
     value = units_total / (ms_per_step * 1e-3)
 
     # ---- e2e: public API with pinned HOST buffers, H2D + kernel + D2H in the timed region ----
