@@ -34,6 +34,38 @@ def test_struct_layouts_match_header_sizes(lib):
     assert lib.zodi_abi_version() == _cabi.ABI_VERSION
 
 
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays include/zodi_b200.h out == the ctypes mirror."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc unavailable")
+    structs = {"zodi_component_desc": _cabi.ComponentDesc, "zodi_model_desc": _cabi.ModelDesc,
+               "zodi_eval_args": _cabi.EvalArgs, "zodi_ephemeris_desc": _cabi.EphemerisDesc,
+               "zodi_healpix_args": _cabi.HealpixArgs, "zodi_lonlat_args": _cabi.LonLatArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "zodi_b200.h"', "int main(void) {"]
+    for cname, ctype in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for field, _ in ctype._fields_:
+            lines.append(f'  printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        ctype = structs[cname]
+        expect = C.sizeof(ctype) if field == "size" else getattr(ctype, field).offset
+        assert int(value) == expect, (cname, field, value, expect)
+        seen += 1
+    assert seen == sum(len(t._fields_) + 1 for t in structs.values())
+    assert _cabi.MAX_COMPS == 16 and _cabi.MAX_PEERS == 8
+
+
 def test_sass_is_sm100a_only():
     import subprocess
 
