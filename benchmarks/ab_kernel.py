@@ -18,7 +18,10 @@ CASES = (("planck18", 857.0, "GHz", 2048, "fp32"), ("dirbe", 25.0, "um", 1024, "
 
 def main():
     reps = int(os.environ.get("AB_REPS", 15))
+    only = os.environ.get("AB_ONLY", "")  # substring filter on the case label, e.g. AB_ONLY=fp64
     for name, x, unit, nside, precision in CASES:
+        if only and only not in f"{name} {x}{unit} nside{nside} {precision}":
+            continue
         model = zp.Model(zp.Quantity(x, unit), name=name, precision=precision)
         out = None
         ts = []

@@ -105,8 +105,11 @@ ZODI_HD void band_accumulate(Real& accB, Real& accS, Real wB, Real wF, Real xh, 
                              Real rinv, Real rinv_rad, Real bx, Real by, Real bz, Real c3) {
     using M = Math<Real>;
     const Real sz = M::fma_(xh, bx, M::fma_(yh, by, zh * bz)) * rinv;  // sign irrelevant (even powers)
-    const Real s2 = sz * sz, s4 = s2 * s2, s6 = s4 * s2;
-    if (warp_any(s6 <= M::kEx2Underflow)) {
+    const Real s2 = sz * sz;
+    // decided on s^2 (kS2Underflow): lanes with s^6 beyond the underflow point inside an executing warp get
+    // their exact 0 from exp2_neg_ itself
+    if (warp_any(s2 <= M::kS2Underflow)) {
+        const Real s4 = s2 * s2, s6 = s4 * s2;
         const Real n = (M::exp2_neg_(s6) * M::fma_(s4, c3, Real(1))) * rinv_rad;
         accB = M::fma_(wB, n, accB);
         if (SCATTER) accS = M::fma_(wF, n, accS);
@@ -164,6 +167,7 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
     Real h, mid;
     los_interval<Real>(G, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, h, mid);
     Real aB0 = 0, aB1 = 0, aB2 = 0, aB3 = 0, aS0 = 0, aS1 = 0, aS2 = 0, aS3 = 0;
+    const Real by_min = M::min_(K.b_y[0], M::min_(K.b_y[1], K.b_y[2]));
     // Warp-uniform trip count: the body contains warp votes (warp_any), so every lane must run the
     // same number of iterations even when n_nodes is not a multiple of L; surplus iterations
     // re-evaluate the last node with weight 0.
@@ -175,13 +179,21 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
                                                               G.uz, G.ox, G.oy, G.oz);
         // bands: centred on the Sun -> share R
         const Real rinv = M::rsqrt_(s.Rh2);
-        const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
-        const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
-        const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
         const Real wB = nw.b * s.B, wF = SCATTER ? nw.b * s.F : Real(0);
-        band_accumulate<Real, SCATTER>(aB1, aS1, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad1, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
-        band_accumulate<Real, SCATTER>(aB2, aS2, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad2, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
-        band_accumulate<Real, SCATTER>(aB3, aS3, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad3, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        // all radial cut-off factors are exactly 1 once R^2 min(b_y) >= kRadialOne in every lane (b_y > 0, the
+        // products are monotonic in b_y): one vote then replaces the per-band ones and rinv * 1 is rinv
+        if (!warp_any(s.Rh2 * by_min < M::kRadialOne)) {
+            band_accumulate<Real, SCATTER>(aB1, aS1, wB, wF, s.xh, s.yh, s.zh, rinv, rinv, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+            band_accumulate<Real, SCATTER>(aB2, aS2, wB, wF, s.xh, s.yh, s.zh, rinv, rinv, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+            band_accumulate<Real, SCATTER>(aB3, aS3, wB, wF, s.xh, s.yh, s.zh, rinv, rinv, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        } else {
+            const Real rad1 = band_radial<Real>(s.Rh2, K.b_y[0]);
+            const Real rad2 = band_radial<Real>(s.Rh2, K.b_y[1]);
+            const Real rad3 = SHARE13 ? rad1 : band_radial<Real>(s.Rh2, K.b_y[2]);
+            band_accumulate<Real, SCATTER>(aB1, aS1, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad1, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
+            band_accumulate<Real, SCATTER>(aB2, aS2, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad2, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
+            band_accumulate<Real, SCATTER>(aB3, aS3, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad3, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        }
         // cloud
         const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
         const Real Rc2 = M::fma_(xc, xc, M::fma_(yc, yc, zc * zc));
