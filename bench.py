@@ -42,7 +42,9 @@ EXEC_ISSUE_PER_UNIT = 153.7 / 8   # warp-instruction issue slots
 EXEC_MUFU_PER_UNIT = 21.0 / 8     # XU-pipe instructions (8 cycles each per SM sub-partition)
 EXEC_FMA_CYCLES_PER_UNIT = 130.9 / 8  # FMA-pipe cycles (packed FFMA2/FMUL2/FADD2 take 2)
 # Same for the fp64 kernel, profiles/r1_ncu_fp64_planck18_nside1024.md: 80.3 thread-instructions per
-# evaluation of which 43.5 % go to the FP64 pipe (one warp instruction per two issue cycles).
+# evaluation of which 43.5 % go to the FP64 pipe (one warp instruction per two issue cycles).  The capture
+# predates the band-skip / radial early-out step of the scalar kernels (-3.9 % time), so the utilisations
+# derived from it are upper bounds.
 EXEC64_ISSUE_PER_UNIT = 80.3
 EXEC64_FP64_PER_UNIT = 80.3 * 0.435
 # DRAM traffic per line of sight of the fp32 kernel with array inputs, `ncu --set full`
