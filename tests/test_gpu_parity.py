@@ -325,12 +325,13 @@ def test_evaluate_lonlat_equals_array_seam(name, x, unit, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_multi_device_host_sharding_bitwise(precision):
+def test_multi_device_host_sharding_bitwise(precision, monkeypatch):
     """Model(devices=[...]) splits host arrays over several device handles driven by threads of one
     process (here: all on GPU 0, or spread over the GPUs present); bit-identical to one handle,
     including time-ordered data whose observers straddle a cutoff sphere (global early-out flags)."""
     import torch
 
+    monkeypatch.setattr(engine.MultiDeviceModel, "MIN_LOS_PER_DEVICE", 1)  # split the small golden case too
     devices = [i % torch.cuda.device_count() for i in range(3)]
     one = zp.Model(zp.Quantity(25.0, "um"), precision=precision, device=0)
     many = zp.Model(zp.Quantity(25.0, "um"), precision=precision, devices=devices)

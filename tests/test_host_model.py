@@ -187,3 +187,29 @@ def test_evaluate_requires_skycoord_like():  # reference tests/test_evaluate.py:
 
     with pytest.raises(ValueError):
         m.evaluate(NoTime())
+
+
+def test_lonlat_argument_packing():
+    """The spherical-coordinate arguments reach the C struct unchanged (no GPU needed)."""
+    import ctypes as C
+
+    from zodipy_b200 import _cabi, engine
+
+    lon, lat = np.linspace(0.0, 6.0, 7), np.linspace(-1.5, 1.5, 7)
+    rot = np.arange(9.0).reshape(3, 3)
+    ll = engine._LonLat(lon[::1], lat, rot)
+    base = _cabi.EvalArgs()
+    base.n = 7
+    packed = ll.pack(base)
+    assert packed.base.n == 7 and packed.has_rot == 1 and list(packed.rot) == list(range(9))
+    assert packed.lon == ll.lon.ctypes.data and packed.lat == ll.lat.ctypes.data
+    got = np.ctypeslib.as_array(C.cast(packed.lon, C.POINTER(C.c_double)), shape=(7,))
+    np.testing.assert_array_equal(got, lon)
+    assert engine._LonLat(lon, lat).pack(base).has_rot == 0
+    # non-contiguous / non-float64 inputs are copied into contiguous float64
+    ll2 = engine._LonLat(np.arange(14, dtype=np.float32)[::2], lat)
+    assert ll2.lon.dtype == np.float64 and ll2.lon.flags.c_contiguous and ll2.n == 7
+    with pytest.raises(ValueError):
+        engine._LonLat(lon, lat[:-1])
+    with pytest.raises(ValueError):
+        engine._LonLat(lon, lat, np.eye(2))

@@ -141,6 +141,7 @@ def test_single_process_multi_device_host_sharding(monkeypatch, n_devices, case_
             pass
 
     monkeypatch.setattr(engine, "DeviceModel", StubDeviceModel)
+    monkeypatch.setattr(engine.MultiDeviceModel, "MIN_LOS_PER_DEVICE", 1)  # the golden cases are small
     multi = engine.MultiDeviceModel(spec, list(range(n_devices)))
     n = a["u"].shape[1]
     got = multi.evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
@@ -162,3 +163,8 @@ def test_single_process_multi_device_host_sharding(monkeypatch, n_devices, case_
         multi.evaluate(a["u"], a["obs"][:, :2] if per_sample else np.ones((3, 2)))
     with pytest.raises(ValueError):
         engine.MultiDeviceModel(spec, [])
+    # small jobs stay on the first device
+    monkeypatch.setattr(engine.MultiDeviceModel, "MIN_LOS_PER_DEVICE", 1 << 15)
+    calls.clear()
+    np.testing.assert_array_equal(multi.evaluate(a["u"], a["obs"], a["earth"], return_comps=True), a["emission"])
+    assert [c[0] for c in calls] == [0]

@@ -552,6 +552,8 @@ class MultiDeviceModel:
     ctypes releases the GIL during the calls, so plain Python threads keep all devices busy.
     """
 
+    MIN_LOS_PER_DEVICE = 1 << 15  # below this per device the split costs more than it saves
+
     def __init__(self, spec: dict, devices):
         devices = [int(d) for d in devices]
         if not devices:
@@ -589,7 +591,12 @@ class MultiDeviceModel:
         if obs.shape[1] not in (1, n) or earth.shape[1] not in (1, n):
             raise ValueError("obs/earth must hold one position or one per line of sight")
         flags = self.models[0].outside_flags(obs) if outside_flags is None else outside_flags
-        shards = [(m, lo, hi) for m, (lo, hi) in zip(self.models, split_bounds(n, len(self.models))) if hi > lo]
+        # small jobs are latency-bound: one device, no thread hand-off
+        parts = len(self.models) if n >= self.MIN_LOS_PER_DEVICE * len(self.models) else 1
+        shards = [(m, lo, hi) for m, (lo, hi) in zip(self.models, split_bounds(n, parts)) if hi > lo]
+        if len(shards) == 1:
+            call(shards[0][0], 0, n, obs, earth, out, flags)
+            return out
 
         def work(item):
             m, lo, hi = item
