@@ -66,7 +66,9 @@ static void run_kelsall(const KelsallModel<Real>& K, const std::vector<Pair<Real
     }
 }
 
-// Packed (two lines of sight per "thread") routines of zodi_kelsall_x2.cuh, fp32 thermal-only.
+// Packed (two lines of sight per "thread") routines of zodi_kelsall_x2.cuh (fp32), L lanes per pair
+// emulated serially; partial sums are added in lane order.
+template <int L>
 static void run_kelsall_x2(const KelsallModel<float>& K, const std::vector<Pair<float>>& tab,
                            const std::vector<Pair<float>>& nodes, int64_t n, const double* u,
                            const double* obs, int64_t n_obs, const double* earth, int64_t n_earth,
@@ -78,25 +80,37 @@ static void run_kelsall_x2(const KelsallModel<float>& K, const std::vector<Pair<
     }
     for (int64_t j0 = 0; j0 < n; j0 += 2) {
         const int64_t jj[2] = {j0, j0 + 1 < n ? j0 + 1 : j0};
-        LosGeometry<float> G[2];
-        double ex[2], ey[2];
+        LosPre P[2];
         for (int q = 0; q < 2; ++q) {
             const int64_t j = jj[q], jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
-            G[q] = los_geometry<float>(u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo]);
-            ex[q] = earth[je];
-            ey[q] = earth[n_earth + je];
+            if (K.n_comps == 6)
+                P[q] = los_pre<true>(K, u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo],
+                                     earth[je], earth[n_earth + je], mask);
+            else
+                P[q] = los_pre<false>(K, u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo],
+                                      earth[je], earth[n_earth + je], mask);
         }
-        auto emit2 = [&](int ci, float a, float b) { out[ci * n + jj[0]] = a; out[ci * n + jj[1]] = b; };
-#define ZX2(SH, SC) kelsall_group_a_x2<SH, SC>(K, tab.data(), nodes.data(), G[0], G[1], mask, emit2)
-        if (K.share13) { if (K.scatter) ZX2(true, true); else ZX2(true, false); }
-        else { if (K.scatter) ZX2(false, true); else ZX2(false, false); }
+        double acc[6][2] = {{0.0}};  // like run_kelsall: lane partials are added in double
+        for (int sub = 0; sub < L; ++sub) {
+            auto emit2 = [&](int ci, float a, float b) { acc[ci][0] += (double)a; acc[ci][1] += (double)b; };
+#define ZX2(SH, SC) kelsall_group_a_x2<SH, SC, L>(K, tab.data(), nodes.data(), P[0], P[1], sub, emit2)
+            if (K.share13) { if (K.scatter) ZX2(true, true); else ZX2(true, false); }
+            else { if (K.scatter) ZX2(false, true); else ZX2(false, false); }
 #undef ZX2
-        if (K.n_comps == 6)
-            for (int q = 1; q >= 0; --q) {
-                auto put = [&](float r, float f) { out[4 * n + jj[q]] = r; out[5 * n + jj[q]] = f; };
-                if (K.scatter) kelsall_ring_feature_packed<true>(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask, put);
-                else kelsall_ring_feature_packed<false>(K, tab.data(), nodes.data(), G[q], ex[q], ey[q], mask, put);
+            if (K.n_comps == 6) {
+                auto ring = [&](float a, float b) { emit2(4, a, b); };
+                auto feat = [&](float a, float b) { emit2(5, a, b); };
+                if (K.scatter) {
+                    kelsall_ring_x2<true, L>(K, tab.data(), nodes.data(), P[0], P[1], sub, ring);
+                    kelsall_feature_x2<true, L>(K, tab.data(), nodes.data(), P[0], P[1], sub, feat);
+                } else {
+                    kelsall_ring_x2<false, L>(K, tab.data(), nodes.data(), P[0], P[1], sub, ring);
+                    kelsall_feature_x2<false, L>(K, tab.data(), nodes.data(), P[0], P[1], sub, feat);
+                }
             }
+        }
+        for (int c = 0; c < K.n_comps; ++c)
+            for (int q = 1; q >= 0; --q) out[c * n + jj[q]] = acc[c][q];
     }
 }
 
@@ -139,7 +153,12 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
         KelsallModel<float> k32;
         narrow_kelsall(k64, k32);
         if (fast == 2) {
-            run_kelsall_x2(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out);
+            switch (lanes) {
+                case 2: run_kelsall_x2<2>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out); break;
+                case 4: run_kelsall_x2<4>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out); break;
+                case 8: run_kelsall_x2<8>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out); break;
+                default: run_kelsall_x2<1>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out);
+            }
             return 2;
         }
         run_kelsall<float>(k32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);

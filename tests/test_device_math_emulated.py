@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emu", "zodi_emu.cpp")
 LIB = os.path.join(HERE, "host_emu", "libzodi_emu.so")
 DEPS = [SRC] + [os.path.join(HERE, "..", "zodipy_b200", "csrc", f)
-                for f in ("zodi_device.cuh", "zodi_model_build.hpp")]
+                for f in ("zodi_device.cuh", "zodi_model_build.hpp", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -74,14 +74,16 @@ def test_fused_routines_match_reference(emu, case_id, precision):
     assert max_rel_comps(em, a["emission"], floor=floor) <= tol
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 8])
 @pytest.mark.parametrize("case_id", case_ids())
-def test_packed_routines_equal_scalar_fused(emu, case_id):
-    """Packed routines (zodi_kelsall_x2.cuh) perform the same operations as the scalar fused ones."""
+def test_packed_routines_equal_scalar_fused(emu, case_id, lanes):
+    """Packed routines (zodi_kelsall_x2.cuh; cloud + bands, ring | ring, feature | feature, any lane
+    split) perform the same operations as the scalar fused ones."""
     case, a = golden_case(case_id)
-    packed, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=2)
+    packed, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, lanes, fast=2)
     if used != 2:
-        pytest.skip("not eligible for the packed routines (generic layout or scattering)")
-    scalar, _ = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=1)
+        pytest.skip("not eligible for the packed routines (generic layout)")
+    scalar, _ = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, lanes, fast=1)
     # bit-identical on the GPU (ex2.approx.ftz flushes to 0); the host's libm returns denormals
     # where one lane of a pair is beyond the underflow threshold, hence the 1e-37 allowance
     np.testing.assert_allclose(packed, scalar, rtol=0, atol=1e-37)

@@ -405,6 +405,36 @@ def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
     ref = oracle.evaluate(model.spec, u[:, sel], obs[:, sel], EARTH_20220114)
     assert max_rel_total(a[:, sel], ref) <= TOL_FP32
     assert max_rel_comps(a[:, sel], ref, floor=COMP_FLOOR_FP32) <= TOL_FP32
+    # mid-size input: both kernels split the nodes of a line of sight over 8 lanes (same shuffle tree)
+    m = 30001
+    a = packed.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32", return_comps=True)
+    b = scalar.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32", return_comps=True)
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("threads", [128, 256])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+def test_packed_kernel_lane_splits(lanes, threads, monkeypatch):
+    """Every shape of the packed kernel (lanes per pair of lines of sight x CTA size): same results up to
+    the summation order of the lane partials, ragged sizes, per-sample observers, component output."""
+    model = zp.Model(zp.Quantity(25.0, "um"), precision="fp32")
+    dm = model.device_model
+    n = 70001
+    u = fibonacci_sphere(n)
+    rng = np.random.default_rng(6)
+    obs = EARTH_20220114 * (1.0 + 0.02 * rng.standard_normal((1, n)))
+    monkeypatch.setenv("ZODI_X2_LANES", "1")
+    monkeypatch.setenv("ZODI_X2_THREADS", "256")
+    base = dm.evaluate(u, obs, EARTH_20220114, precision="fp32", return_comps=True)
+    monkeypatch.setenv("ZODI_X2_LANES", str(lanes))
+    monkeypatch.setenv("ZODI_X2_THREADS", str(threads))
+    for m in (n, 1, 2, 3, 255, 513, 4097):
+        got = dm.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32", return_comps=True)
+        np.testing.assert_allclose(got, base[:, :m], rtol=3e-6, atol=1e-12)
+        tot = dm.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32")
+        np.testing.assert_allclose(tot, got.sum(axis=0), rtol=1e-6)
+    if lanes == 1:
+        np.testing.assert_array_equal(dm.evaluate(u, obs, EARTH_20220114, precision="fp32", return_comps=True), base)
 
 
 def _tod_inputs(n, seed=0):

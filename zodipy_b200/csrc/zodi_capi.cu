@@ -16,15 +16,79 @@
 #include <thread>
 #include <vector>
 
-#include "zodi_kernels.cuh"
+#include "zodi_launch.hpp"
+#include "zodi_misc_kernels.cuh"
 #include "zodi_model_build.hpp"
 
 using namespace zodi;
 
+namespace zodi {
+
+std::atomic<int64_t> g_launches{0};
+
+int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load();
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n);
+    }
+    return n;
+}
+
+int pick_lanes(int64_t n, int n_nodes) {
+    // enough threads to fill every SM's 2048 resident threads; never more lanes than nodes
+    const int64_t fill = (int64_t)sm_count() * 2048;
+    int L = 1;
+    while (L < 32 && n * L < fill && 2 * L <= n_nodes) L *= 2;
+    return L;
+}
+
+// Packed kernels: a thread works on a PAIR of lines of sight, 1280 threads are resident per SM (5 CTAs of
+// 256 / 10 of 128).  L lanes per pair: the smallest count that gives every resident thread slot work.
+// ZODI_X2_LANES / ZODI_X2_THREADS force a shape (measurements, tests).
+PackedShape pick_packed_shape(int64_t n, int n_nodes) {
+    const char* el = std::getenv("ZODI_X2_LANES");
+    const char* et = std::getenv("ZODI_X2_THREADS");
+    const int env_lanes = el ? std::atoi(el) : 0, env_threads = et ? std::atoi(et) : 0;
+    PackedShape s;
+    s.threads = env_threads == 128 ? 128 : (env_threads == 256 ? 256 : kPackedDefaultThreads);
+    if (env_lanes == 1 || env_lanes == 2 || env_lanes == 4 || env_lanes == 8) {
+        s.lanes = env_lanes;
+        return s;
+    }
+    const int64_t pairs = (n + 1) / 2, fill = (int64_t)sm_count() * 1280;
+    s.lanes = 1;
+    while (s.lanes < 8 && pairs * s.lanes < fill && 2 * s.lanes <= n_nodes) s.lanes *= 2;
+    return s;
+}
+
+cudaError_t launch_kelsall_packed_l1(const KelsallModel<float>&, const LaunchArgs&, const Pair<float>*,
+                                     const Pair<float>*, int, cudaStream_t);
+cudaError_t launch_kelsall_packed_l2(const KelsallModel<float>&, const LaunchArgs&, const Pair<float>*,
+                                     const Pair<float>*, int, cudaStream_t);
+cudaError_t launch_kelsall_packed_l4(const KelsallModel<float>&, const LaunchArgs&, const Pair<float>*,
+                                     const Pair<float>*, int, cudaStream_t);
+cudaError_t launch_kelsall_packed_l8(const KelsallModel<float>&, const LaunchArgs&, const Pair<float>*,
+                                     const Pair<float>*, int, cudaStream_t);
+
+cudaError_t launch_kelsall_packed(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
+                                  const Pair<float>* nodes, PackedShape shape, cudaStream_t stream) {
+    switch (shape.lanes) {
+        case 1: return launch_kelsall_packed_l1(K, a, tab, nodes, shape.threads, stream);
+        case 2: return launch_kelsall_packed_l2(K, a, tab, nodes, shape.threads, stream);
+        case 4: return launch_kelsall_packed_l4(K, a, tab, nodes, shape.threads, stream);
+        default: return launch_kelsall_packed_l8(K, a, tab, nodes, shape.threads, stream);
+    }
+}
+
+}  // namespace zodi
+
 namespace {
 
 thread_local std::string g_last_error;
-std::atomic<int64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -144,6 +208,8 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     narrow_model(m->m64, m->m32);
     m->kelsall_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes &&
                     build_kelsall_model(*d, m->k64);
+    const char* ntp = std::getenv("ZODI_NO_RING_TPOLY");  // testing knob: ring temperature by the power law
+    if (m->kelsall_ok && ntp && ntp[0] == '1') m->k64.ring_poly_ok = 0;
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
     const char* fg = std::getenv("ZODI_FORCE_GENERIC");
     m->force_generic = (fg && fg[0] == '1');
@@ -199,153 +265,28 @@ void flags_from_r(const zodi_model_s* m, double r_max, uint8_t* flags) {
     }
 }
 
-int pick_lanes(int64_t n, int n_nodes) {
-    // enough threads to fill 148 SMs x 2048 resident threads; never more lanes than nodes
-    int L = 1;
-    while (L < 32 && n * L < 148 * 2048 && 2 * L <= n_nodes) L *= 2;
-    return L;
-}
-
-template <typename Real, int L>
-cudaError_t launch_generic_L(const DevModel<Real>& M, const LaunchArgs& a, const Pair<Real>* tab,
-                             const Pair<Real>* nodes, cudaStream_t stream) {
-    const int per_cta = kThreads / L;
-    const int64_t grid = (a.n + per_cta - 1) / per_cta;
-    const size_t smem = (size_t)(M.n_temps + M.n_nodes) * sizeof(Pair<Real>);
-    zodi_los_generic_kernel<Real, L><<<(unsigned)grid, kThreads, smem, stream>>>(M, a, tab, nodes);
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
-}
-
-template <typename Real>
-cudaError_t launch_generic(const DevModel<Real>& M, const LaunchArgs& a, const Pair<Real>* tab,
-                           const Pair<Real>* nodes, cudaStream_t stream) {
-    switch (pick_lanes(a.n, M.n_nodes)) {
-        case 1: return launch_generic_L<Real, 1>(M, a, tab, nodes, stream);
-        case 2: return launch_generic_L<Real, 2>(M, a, tab, nodes, stream);
-        case 4: return launch_generic_L<Real, 4>(M, a, tab, nodes, stream);
-        case 8: return launch_generic_L<Real, 8>(M, a, tab, nodes, stream);
-        case 16: return launch_generic_L<Real, 16>(M, a, tab, nodes, stream);
-        default: return launch_generic_L<Real, 32>(M, a, tab, nodes, stream);
-    }
-}
-
-template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13, int L>
-cudaError_t launch_kelsall_L(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
-                             const Pair<Real>* nodes, cudaStream_t stream) {
-    // fp64 variants of 128 threads x 9 CTAs/SM (56 registers) and 256 x 5 (48 registers, spills)
-    // measured within 1 % of this shape on B200: the kernel is bound by issue slots, not occupancy.
-    const int per_cta = kThreads / L;
-    const int64_t grid = (a.n + per_cta - 1) / per_cta;
-    zodi_los_kelsall_kernel<Real, HAS_RF, SCATTER, SHARE13, L>
-        <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
-}
-
-template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13>
-cudaError_t launch_kelsall_RSS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
-                               const Pair<Real>* nodes, cudaStream_t stream) {
-    if (pick_lanes(a.n, K.n_nodes) == 1)
-        return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 1>(K, a, tab, nodes, stream);
-    return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 8>(K, a, tab, nodes, stream);
-}
-
-template <typename Real, bool HAS_RF, bool SCATTER>
-cudaError_t launch_kelsall_RS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
-                              const Pair<Real>* nodes, cudaStream_t stream) {
-    if (K.share13) return launch_kelsall_RSS<Real, HAS_RF, SCATTER, true>(K, a, tab, nodes, stream);
-    return launch_kelsall_RSS<Real, HAS_RF, SCATTER, false>(K, a, tab, nodes, stream);
-}
-
-template <typename Real>
-cudaError_t launch_kelsall(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
-                           const Pair<Real>* nodes, cudaStream_t stream) {
-    if (K.n_comps == 6) {
-        if (K.scatter) return launch_kelsall_RS<Real, true, true>(K, a, tab, nodes, stream);
-        return launch_kelsall_RS<Real, true, false>(K, a, tab, nodes, stream);
-    }
-    if (K.scatter) return launch_kelsall_RS<Real, false, true>(K, a, tab, nodes, stream);
-    return launch_kelsall_RS<Real, false, false>(K, a, tab, nodes, stream);
-}
-
-template <bool HAS_RF, bool SHARE13, bool SCATTER>
-cudaError_t launch_kelsall_x2(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
-                              const Pair<float>* nodes, cudaStream_t stream) {
-    const int64_t grid = (a.n + 2 * kThreads - 1) / (2 * kThreads);
-    // 5 CTAs/SM (48 registers): cloud+bands only measured 5 % faster than 4 CTAs/SM (60 registers) and
-    // 0.4 % faster than 6 (40 registers); with the ring/feature loops 5 CTAs/SM is 0.8 % faster than 4 (64
-    // registers) - the spills it causes sit in the per-line-of-sight prologue / epilogue, not in the node
-    // loops.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  The macros exist for
-    // A/B builds (benchmarks/ab_kernel.py).
-#ifndef ZODI_X2_CTAS_THERMAL
-#define ZODI_X2_CTAS_THERMAL 5
-#endif
-#ifndef ZODI_X2_CTAS_RF
-#define ZODI_X2_CTAS_RF 5
-#endif
-    constexpr int kMinCtas = SCATTER ? 3 : (HAS_RF ? ZODI_X2_CTAS_RF : ZODI_X2_CTAS_THERMAL);
-    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, kMinCtas>
-        <<<(unsigned)grid, kThreads, 0, stream>>>(K, a, tab, nodes);
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
-}
-
-template <bool HAS_RF, bool SHARE13>
-cudaError_t launch_kelsall_x2_S(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
-                                const Pair<float>* nodes, cudaStream_t stream) {
-    return K.scatter ? launch_kelsall_x2<HAS_RF, SHARE13, true>(K, a, tab, nodes, stream)
-                     : launch_kelsall_x2<HAS_RF, SHARE13, false>(K, a, tab, nodes, stream);
-}
-
-template <typename Real, int NB>
-cudaError_t launch_multiband_NB(const MultiBandModel<Real>& MB, const LaunchArgs& a, const Pair<Real>* tabs,
-                                const Pair<Real>* nodes, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((a.n + kThreads - 1) / kThreads);
-    const bool rf = MB.base.n_comps == 6, sc = MB.base.scatter != 0;
-    if (rf && sc) zodi_los_multiband_kernel<Real, NB, true, true><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
-    else if (rf) zodi_los_multiband_kernel<Real, NB, true, false><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
-    else if (sc) zodi_los_multiband_kernel<Real, NB, false, true><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
-    else zodi_los_multiband_kernel<Real, NB, false, false><<<grid, kThreads, 0, stream>>>(MB, a, tabs, nodes);
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
-}
-
-template <typename Real>
-cudaError_t launch_multiband(const MultiBandModel<Real>& MB, const LaunchArgs& a, const Pair<Real>* tabs,
-                             const Pair<Real>* nodes, cudaStream_t stream) {
-    if (MB.n_bands <= 4) return launch_multiband_NB<Real, 4>(MB, a, tabs, nodes, stream);
-    if (MB.n_bands <= 8) return launch_multiband_NB<Real, 8>(MB, a, tabs, nodes, stream);
-    return launch_multiband_NB<Real, 16>(MB, a, tabs, nodes, stream);
-}
-
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     if (m->mb_bands > 0) {
-        if (precision == ZODI_FP32) return launch_multiband<float>(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
-        return launch_multiband<double>(m->mb64, a, m->d_mbtab64, m->d_nodes64, stream);
+        if (precision == ZODI_FP32) return launch_multiband_f32(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+        return launch_multiband_f64(m->mb64, a, m->d_mbtab64, m->d_nodes64, stream);
     }
     if (m->kelsall_ok && !m->force_generic) {
-        // packed-fp32 kernel: fp32, thermal-only, enough lines of sight for thread-per-pair mapping
-        if (precision == ZODI_FP32 && !m->no_x2 && pick_lanes(a.n / 2, m->k32.n_nodes) == 1) {
-            const KelsallModel<float>& K = m->k32;
-            if (K.n_comps == 6)
-                return K.share13 ? launch_kelsall_x2_S<true, true>(K, a, m->d_table32, m->d_nodes32, stream)
-                                 : launch_kelsall_x2_S<true, false>(K, a, m->d_table32, m->d_nodes32, stream);
-            return K.share13 ? launch_kelsall_x2_S<false, true>(K, a, m->d_table32, m->d_nodes32, stream)
-                             : launch_kelsall_x2_S<false, false>(K, a, m->d_table32, m->d_nodes32, stream);
-        }
-        if (precision == ZODI_FP32) return launch_kelsall<float>(m->k32, a, m->d_table32, m->d_nodes32, stream);
-        return launch_kelsall<double>(m->k64, a, m->d_table64, m->d_nodes64, stream);
+        // packed-fp32 kernels: every fp32 evaluation of a Kelsall-family model
+        if (precision == ZODI_FP32 && !m->no_x2)
+            return launch_kelsall_packed(m->k32, a, m->d_table32, m->d_nodes32,
+                                         pick_packed_shape(a.n, m->k32.n_nodes), stream);
+        if (precision == ZODI_FP32) return launch_kelsall_f32(m->k32, a, m->d_table32, m->d_nodes32, stream);
+        return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }
-    if (precision == ZODI_FP32) return launch_generic<float>(m->m32, a, m->d_table32, m->d_nodes32, stream);
-    return launch_generic<double>(m->m64, a, m->d_table64, m->d_nodes64, stream);
+    if (precision == ZODI_FP32) return launch_generic_f32(m->m32, a, m->d_table32, m->d_nodes32, stream);
+    return launch_generic_f64(m->m64, a, m->d_table64, m->d_nodes64, stream);
 }
 
 int max_r_device(zodi_model_s* m, const double* d_obs, int64_t n_obs, int64_t stride,
                  cudaStream_t stream, double* r_max) {
     CU_CHECK(cudaMemsetAsync(m->d_scratch, 0, sizeof(unsigned long long), stream));
-    const int grid = (int)std::min<int64_t>((n_obs + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<int64_t>((n_obs + 255) / 256, (int64_t)sm_count() * 8);
     zodi_max_r2_kernel<<<grid, 256, 0, stream>>>(d_obs, n_obs, stride, m->d_scratch);
     g_launches.fetch_add(1);
     CU_CHECK(cudaGetLastError());
@@ -850,7 +791,7 @@ int zodi_ephemeris_stats(zodi_ephemeris_t e, const double* t, int64_t n, int32_t
     std::memset(&la, 0, sizeof(la));
     la.n = n;
     set_ephemeris(la, e, d_t);
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
     zodi_ephemeris_stats_kernel<<<grid, 256, 0, st>>>(la, e->d_stats, reinterpret_cast<unsigned long long*>(e->d_stats + 1));
     g_launches.fetch_add(1);
     CU_CHECK(cudaGetLastError());
@@ -1161,8 +1102,7 @@ int zodi_peer_buffer_free(int device, void* ptr) {
 const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
     if (!m) return "";
     if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";
-    if (precision == ZODI_FP32 && !m->no_x2 && pick_lanes(n / 2, m->k32.n_nodes) == 1)
-        return "zodi_los_kelsall_x2_kernel";
+    if (precision == ZODI_FP32 && !m->no_x2) return "zodi_los_kelsall_x2_kernel";
     return "zodi_los_kelsall_kernel";
 }
 
@@ -1183,7 +1123,7 @@ int zodi_device_math(int device, int32_t op, int64_t n, const double* x, double 
         return fail(ZODI_ERR_NOMEM, "cannot allocate %lld doubles", (long long)n);
     }
     cudaMemcpy(d_x, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
     zodi_device_math_kernel<<<grid, 256>>>(op, n, d_x, aux, d_y);
     g_launches.fetch_add(1);
     cudaError_t err = cudaGetLastError();

@@ -122,9 +122,11 @@ ZODI_HD TableRef table_ref(const Pair<float>* tab) {
     return r;
 }
 
-// Table lookup for two temperatures (same arithmetic as table_at<float>).
+// Table lookup for two temperatures (same arithmetic as table_at<float>).  CLAMP = false: the caller
+// guarantees 0 <= t <= t_top (clamping is then the identity).
+template <bool CLAMP = true>
 ZODI_HD F2 table_at2(TableRef ref, F2 t, float t_top) {
-    t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
+    if (CLAMP) t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
     const float magic = 12582912.0f;
     const F2 s = add2(add2(t, -0.5f), magic);
     Pair<float> e0, e1;
@@ -188,17 +190,56 @@ ZODI_HD void band_accumulate2(F2& acc, F2& accS, F2 wB, F2 wF, F2 xh, F2 yh, F2 
     }
 }
 
-// Group A (cloud + band1..3, thermal only) for two lines of sight; emit(ci, value_a, value_b).
-template <bool SHARE13, bool SCATTER, typename Emit>
+// Everything the packed node loops need of one line of sight, in single precision: the product of the
+// fp64 per-line-of-sight prologue (direction, positions, ray / sphere ranges, Earth longitude).  With
+// L > 1 lanes per pair of lines of sight the prologue of a line of sight is computed by ONE lane and
+// handed to the others by warp shuffles (it used to be replicated in every lane).
+struct LosPre {
+    float ux, uy, uz, ox, oy, oz;
+    float hA, midA;            // cloud + bands: half-range and mid-point of the interval (brightness.py:41)
+    float hR, midR, hF, midF;  // ring, feature
+    float cr, sr;              // feature: cos / sin of -(theta_earth + theta_0), see feature_rotation()
+};
+constexpr int kLosPreFloats = 14;
+static_assert(sizeof(LosPre) == kLosPreFloats * sizeof(float), "LosPre is shuffled float by float");
+
+template <bool HAS_RF>
+ZODI_HD LosPre los_pre(const KelsallModel<float>& K, double ux, double uy, double uz, double ox, double oy,
+                       double oz, double ex, double ey, uint32_t outside_mask) {
+    const LosGeometry<float> G = los_geometry<float>(ux, uy, uz, ox, oy, oz);
+    LosPre P;
+    P.ux = G.ux; P.uy = G.uy; P.uz = G.uz; P.ox = G.ox; P.oy = G.oy; P.oz = G.oz;
+    los_interval<float>(G, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, P.hA, P.midA);
+    P.hR = P.midR = P.hF = P.midF = 0.f;
+    P.cr = 1.f; P.sr = 0.f;
+    if (HAS_RF) {
+        los_interval<float>(G, K.cutR_in, K.cutR_out, (outside_mask >> 8) & 1u, (outside_mask >> 9) & 1u, P.hR, P.midR);
+        los_interval<float>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, P.hF, P.midF);
+        feature_rotation<float>(ex, ey, K.f_cos0, K.f_sin0, P.cr, P.sr);  // ring / feature are Sun-centred
+    }
+    return P;
+}
+
+// Node k0 + sub of a rule split over L lanes, with a warp-uniform trip count (the loop bodies contain
+// warp votes): surplus iterations re-evaluate the last node with weight 0.
+template <int L>
+ZODI_HD Pair<float> lane_node(const Pair<float>* nodes, int n_nodes, int k0, int sub) {
+    if (L == 1) return nodes[k0];
+    const int k = k0 + sub;
+    Pair<float> nw = nodes[k < n_nodes ? k : n_nodes - 1];
+    if (k >= n_nodes) nw.b = 0.f;
+    return nw;
+}
+
+// Group A (cloud + band1..3) for two lines of sight; lane `sub` of L takes nodes sub, sub + L, ...
+// emit(ci, partial_a, partial_b): partial quadrature sums times the half-range (the caller adds the
+// L partials of a line of sight).
+template <bool SHARE13, bool SCATTER, int L, typename Emit>
 ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>* tab,
-                                const Pair<float>* nodes, const LosGeometry<float>& Ga,
-                                const LosGeometry<float>& Gb, uint32_t outside_mask, Emit emit) {
-    float ha, mida, hb, midb;
-    los_interval<float>(Ga, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, ha, mida);
-    los_interval<float>(Gb, K.cutA_in, K.cutA_out, outside_mask & 1u, (outside_mask >> 1) & 1u, hb, midb);
-    const F2 h = f2(ha, hb), mid = f2(mida, midb);
-    const F2 ux = f2(Ga.ux, Gb.ux), uy = f2(Ga.uy, Gb.uy), uz = f2(Ga.uz, Gb.uz);
-    const F2 ox = f2(Ga.ox, Gb.ox), oy = f2(Ga.oy, Gb.oy), oz = f2(Ga.oz, Gb.oz);
+                                const Pair<float>* nodes, const LosPre& Pa, const LosPre& Pb, int sub, Emit emit) {
+    const F2 h = f2(Pa.hA, Pb.hA), mid = f2(Pa.midA, Pb.midA);
+    const F2 ux = f2(Pa.ux, Pb.ux), uy = f2(Pa.uy, Pb.uy), uz = f2(Pa.uz, Pb.uz);
+    const F2 ox = f2(Pa.ox, Pb.ox), oy = f2(Pa.oy, Pb.oy), oz = f2(Pa.oz, Pb.oz);
     F2 a0 = f2(0.f), a1 = f2(0.f), a2 = f2(0.f), a3 = f2(0.f);
     F2 s0 = f2(0.f), s1 = f2(0.f), s2 = f2(0.f), s3 = f2(0.f);  // scattering accumulators
     const TableRef tref = table_ref(tab);
@@ -206,8 +247,8 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
 #if defined(__CUDA_ARCH__)
 #pragma unroll kX2Unroll
 #endif
-    for (int k = 0; k < K.n_nodes; ++k) {
-        const Pair<float> nw = nodes[k];
+    for (int k0 = 0; k0 < K.n_nodes; k0 += L) {
+        const Pair<float> nw = lane_node<L>(nodes, K.n_nodes, k0, sub);
         // shared source quantities (node_source<float, false>)
         const F2 R_los = fma2(h, nw.a, mid);
         const F2 xh = fma2(R_los, ux, ox), yh = fma2(R_los, uy, oy), zh = fma2(R_los, uz, oz);
@@ -267,45 +308,97 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     emit(0, r0.x, r0.y); emit(1, r1.x, r1.y); emit(2, r2.x, r2.y); emit(3, r3.x, r3.y);
 }
 
-// Ring and Feature of ONE line of sight in one packed loop: both components repeat the same
-// source-function work on their own quadrature nodes (own cutoff spheres), so the ring rides in
-// the low half and the feature in the high half of every register pair; only the feature's
-// longitude term (atan2) is scalar.  Same operations as kelsall_ring<float,false> /
-// kelsall_feature<float,false> (bit-identical results).  emit(ring_value, feature_value).
-template <bool SCATTER, typename Emit>
-ZODI_HD void kelsall_ring_feature_packed(const KelsallModel<float>& K, const Pair<float>* tab,
-                                         const Pair<float>* nodes, const LosGeometry<float>& G,
-                                         double dex, double dey, uint32_t outside_mask, Emit emit) {
-    float hr, midr, hf, midf;
-    los_interval<float>(G, K.cutR_in, K.cutR_out, (outside_mask >> 8) & 1u, (outside_mask >> 9) & 1u, hr, midr);
-    los_interval<float>(G, K.cutF_in, K.cutF_out, (outside_mask >> 10) & 1u, (outside_mask >> 11) & 1u, hf, midf);
-    const F2 h = f2(hr, hf), mid = f2(midr, midf);
-    float cr, sr;
-    feature_rotation<float>(dex, dey, K.f_cos0, K.f_sin0, cr, sr);  // see kelsall_feature()
-    const F2 R0 = f2(-K.r_R, -K.f_R), c2 = f2(K.r_c2, K.f_c2), c3 = f2(K.r_c3, K.f_c3);
-    const F2 nx = f2(K.rnx, K.fnx), ny = f2(K.rny, K.fny), nz = f2(K.rnz, K.fnz);
+// Polynomial branch of ring_table_coord<float>() for both halves.
+ZODI_HD F2 ring_table_poly2(const KelsallModel<float>& K, F2 d) {
+    const F2 dc = f2(fminf(fmaxf(d.x, -K.r_dmax), K.r_dmax), fminf(fmaxf(d.y, -K.r_dmax), K.r_dmax));
+    F2 p = f2(K.r_tp[kRingPolyTerms - 1]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = kRingPolyTerms - 2; k >= 0; --k) p = fma2(p, dc, f2(K.r_tp[k]));
+    return p;
+}
+
+// Ring of TWO lines of sight per loop (ring | ring in the two halves of every register pair).  Same
+// operations per line of sight as kelsall_ring<float, SCATTER> (bit-identical results).
+template <bool SCATTER, int L, typename Emit>
+ZODI_HD void kelsall_ring_x2(const KelsallModel<float>& K, const Pair<float>* tab, const Pair<float>* nodes,
+                             const LosPre& Pa, const LosPre& Pb, int sub, Emit emit) {
+    const F2 h = f2(Pa.hR, Pb.hR), mid = f2(Pa.midR, Pb.midR);
+    const F2 ux = f2(Pa.ux, Pb.ux), uy = f2(Pa.uy, Pb.uy), uz = f2(Pa.uz, Pb.uz);
+    const F2 ox = f2(Pa.ox, Pb.ox), oy = f2(Pa.oy, Pb.oy), oz = f2(Pa.oz, Pb.oz);
     F2 acc = f2(0.f), accS = f2(0.f);
     const TableRef tref = table_ref(tab);
-    for (int k = 0; k < K.n_nodes; ++k) {
+    for (int k = sub; k < K.n_nodes; k += L) {
         const Pair<float> nw = nodes[k];
         const F2 R_los = fma2(h, nw.a, mid);
-        const F2 xh = fma2(R_los, G.ux, G.ox), yh = fma2(R_los, G.uy, G.oy), zh = fma2(R_los, G.uz, G.oz);
+        const F2 xh = fma2(R_los, ux, ox), yh = fma2(R_los, uy, oy), zh = fma2(R_los, uz, oz);
         const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
-        const F2 t = fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs);
-        const F2 B = table_at2(tref, t, K.t_top);
-        const F2 d = add2(sqrt_2(Rh2), R0);
-        const F2 Zc = fma2(xh, nx, fma2(yh, ny, mul2(zh, nz)));
-        const float xr = fmaf(xh.y, cr, yh.y * sr), yr = fmaf(yh.y, cr, -(xh.y * sr));
-        const float dth = Math<float>::atan2_abs_(yr, xr);  // only dth^2 is used
-        const F2 e = fma2(mul2(d, d), c2, fma2(f2(fabsf(Zc.x), fabsf(Zc.y)), c3, f2(0.f, dth * dth * K.f_c5)));
-        const F2 n = ex2_2(e);
+        const F2 d = add2(sqrt_2(Rh2), -K.r_R);
+        // polynomial path: t stays inside the table by construction (checked by the host, ring_poly_fit)
+        const F2 B = K.ring_poly_ok ? table_at2<false>(tref, ring_table_poly2(K, d), K.t_top)
+                                    : table_at2(tref, fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs), K.t_top);
+        const F2 Zc = fma2(xh, K.rnx, fma2(yh, K.rny, mul2(zh, K.rnz)));
+        const F2 n = ex2_2(fma2(mul2(d, d), K.r_c2, mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), K.r_c3)));
         acc = fma2(mul2(B, nw.b), n, acc);
         if (SCATTER) {
-            const F2 F = scatter_term2(K, f2(G.ux), f2(G.uy), f2(G.uz), xh, yh, zh, rsq_2(Rh2));
+            const F2 F = scatter_term2(K, ux, uy, uz, xh, yh, zh, rsq_2(Rh2));
             accS = fma2(mul2(F, nw.b), n, accS);
         }
     }
-    emit(hr * fmaf(K.aB[4], acc.x, K.aS[4] * accS.x), hf * fmaf(K.aB[5], acc.y, K.aS[5] * accS.y));
+    const F2 r = mul2(h, fma2(acc, K.aB[4], mul2(accS, K.aS[4])));
+    emit(r.x, r.y);
+}
+
+// |atan2(y, x)| for both halves: Math<float>::atan2_abs_ with the polynomial, the quotient and the two
+// reflections on packed instructions (min / max / selects per half).
+ZODI_HD F2 atan2_abs2(F2 y, F2 x) {
+    const F2 ax = f2(fabsf(x.x), fabsf(x.y)), ay = f2(fabsf(y.x), fabsf(y.y));
+    const F2 mn = f2(fminf(ax.x, ay.x), fminf(ax.y, ay.y));
+    const F2 mx = f2(fmaxf(fmaxf(ax.x, ay.x), 1e-30f), fmaxf(fmaxf(ax.y, ay.y), 1e-30f));
+    const F2 a = mul2(mn, f2(atan_rcp(mx.x), atan_rcp(mx.y))), s = mul2(a, a);
+    F2 p = f2(kAtanC8);
+    p = fma2(p, s, kAtanC7); p = fma2(p, s, kAtanC6); p = fma2(p, s, kAtanC5); p = fma2(p, s, kAtanC4);
+    p = fma2(p, s, kAtanC3); p = fma2(p, s, kAtanC2); p = fma2(p, s, kAtanC1); p = fma2(p, s, kAtanC0);
+    F2 r = mul2(a, p);
+    const F2 rc = fma2(r, -1.0f, 1.57079637f);  // pi/2 - r
+    r = f2(ay.x > ax.x ? rc.x : r.x, ay.y > ax.y ? rc.y : r.y);
+    const F2 rs = fma2(r, -1.0f, 3.14159274f);  // pi - r
+    return f2(x.x < 0.0f ? rs.x : r.x, x.y < 0.0f ? rs.y : r.y);
+}
+
+// Feature of TWO lines of sight per loop (feature | feature): rotation, atan polynomial and exponent run
+// packed.  Same operations per line of sight as kelsall_feature<float, SCATTER>.
+template <bool SCATTER, int L, typename Emit>
+ZODI_HD void kelsall_feature_x2(const KelsallModel<float>& K, const Pair<float>* tab, const Pair<float>* nodes,
+                                const LosPre& Pa, const LosPre& Pb, int sub, Emit emit) {
+    const F2 h = f2(Pa.hF, Pb.hF), mid = f2(Pa.midF, Pb.midF);
+    const F2 ux = f2(Pa.ux, Pb.ux), uy = f2(Pa.uy, Pb.uy), uz = f2(Pa.uz, Pb.uz);
+    const F2 ox = f2(Pa.ox, Pb.ox), oy = f2(Pa.oy, Pb.oy), oz = f2(Pa.oz, Pb.oz);
+    const F2 cr = f2(Pa.cr, Pb.cr), sr = f2(Pa.sr, Pb.sr), msr = f2(-Pa.sr, -Pb.sr);
+    F2 acc = f2(0.f), accS = f2(0.f);
+    const TableRef tref = table_ref(tab);
+    for (int k = sub; k < K.n_nodes; k += L) {
+        const Pair<float> nw = nodes[k];
+        const F2 R_los = fma2(h, nw.a, mid);
+        const F2 xh = fma2(R_los, ux, ox), yh = fma2(R_los, uy, oy), zh = fma2(R_los, uz, oz);
+        const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
+        const F2 t = fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs);
+        const F2 B = table_at2(tref, t, K.t_top);
+        const F2 d = add2(sqrt_2(Rh2), -K.f_R);
+        const F2 Zc = fma2(xh, K.fnx, fma2(yh, K.fny, mul2(zh, K.fnz)));
+        const F2 xr = fma2(xh, cr, mul2(yh, sr)), yr = fma2(yh, cr, mul2(xh, msr));  // x * (-s) == -(x * s) exactly
+        const F2 dth = atan2_abs2(yr, xr);  // only dth^2 is used
+        const F2 e = fma2(mul2(d, d), K.f_c2, fma2(f2(fabsf(Zc.x), fabsf(Zc.y)), K.f_c3, mul2(mul2(dth, dth), K.f_c5)));
+        const F2 n = ex2_2(e);
+        acc = fma2(mul2(B, nw.b), n, acc);
+        if (SCATTER) {
+            const F2 F = scatter_term2(K, ux, uy, uz, xh, yh, zh, rsq_2(Rh2));
+            accS = fma2(mul2(F, nw.b), n, accS);
+        }
+    }
+    const F2 r = mul2(h, fma2(acc, K.aB[5], mul2(accS, K.aS[5])));
+    emit(r.x, r.y);
 }
 
 }  // namespace zodi
