@@ -72,6 +72,10 @@ def main() -> None:
     ap.add_argument("--los", type=float, default=0.0, help="lines of sight in the launch")
     ap.add_argument("--evals", type=float, default=0.0, help="evaluations in the launch")
     ap.add_argument("--note", action="append", default=[])
+    ap.add_argument("--counts-json", help="merge this kernel's executed counts per evaluation into this JSON "
+                                          "file (read by bench.py; key = --counts-key)")
+    ap.add_argument("--counts-key")
+    ap.add_argument("--source", help="path of the markdown summary, recorded in the counts file")
     args = ap.parse_args()
 
     m = read_raw(args.report, args.kernel_index)
@@ -98,6 +102,52 @@ def main() -> None:
                    f"{inst * 32 / args.evals:.1f} thread-instructions per evaluation.")
     out.extend(args.note)
     sys.stdout.write("\n".join(out) + "\n")
+    if args.counts_json:
+        write_counts(args, m, rd + wr)
+
+
+def write_counts(args, m, dram_bytes) -> None:
+    """Executed work per evaluation (units of bench.py): warp instructions, XU-pipe warp instructions,
+    FMA / FP64 pipe cycles (SM sub-partition cycles), DRAM bytes per line of sight."""
+    import json
+    import os
+
+    def num(key):
+        return float(m[key][0].replace(",", "")) if key in m and m[key][0] not in ("", "n/a") else None
+
+    if not (args.evals and args.los and args.counts_key):
+        raise SystemExit("--counts-json needs --counts-key, --los and --evals")
+    cycles, n_sm = num("sm__cycles_elapsed.avg"), None
+    inst = num("smsp__inst_executed.sum")
+    sub_cycles = None
+    grid_sms = num("launch__sm_count") or num("device__attribute_multiprocessor_count")
+    if cycles and grid_sms:
+        sub_cycles = cycles * grid_sms * 4
+
+    def pipe_cycles(pct_key):
+        pct = num(pct_key)
+        return None if pct is None or sub_cycles is None else pct / 100.0 * sub_cycles / args.evals
+
+    xu_inst = num("sm__inst_executed_pipe_xu.sum")
+    if xu_inst is None and sub_cycles is not None and num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"):
+        # one XU warp instruction occupies the pipe of an SM sub-partition for 8 cycles
+        xu_inst = num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active") / 100.0 * sub_cycles / 8.0
+    entry = {
+        "source": args.source, "kernel": m["Kernel Name"][0], "n_los": args.los, "evaluations": args.evals,
+        "warp_inst_per_unit": inst / args.evals,
+        "xu_warp_inst_per_unit": None if xu_inst is None else xu_inst / args.evals,
+        "fma_pipe_cycles_per_unit": pipe_cycles("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        "fp64_pipe_cycles_per_unit": pipe_cycles("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+        "dram_bytes_per_los": dram_bytes / args.los,
+    }
+    data = {}
+    if os.path.exists(args.counts_json):
+        with open(args.counts_json) as fh:
+            data = json.load(fh)
+    data[args.counts_key] = entry
+    with open(args.counts_json, "w") as fh:
+        json.dump(data, fh, indent=1, sort_keys=True)
+        fh.write("\n")
 
 
 if __name__ == "__main__":

@@ -46,10 +46,15 @@ int pick_lanes(int64_t n, int n_nodes) {
     return L;
 }
 
-// Packed kernels: a thread works on a PAIR of lines of sight, 1280 threads are resident per SM (5 CTAs of
-// 256 / 10 of 128).  L lanes per pair: the smallest count that gives every resident thread slot work.
-// ZODI_X2_LANES / ZODI_X2_THREADS force a shape (measurements, tests).
-PackedShape pick_packed_shape(int64_t n, int n_nodes) {
+// Packed kernels: a thread works on a PAIR of lines of sight, 1280 threads are resident per SM (10 CTAs
+// of 128).  L lanes per pair split the quadrature nodes; the count minimises a cost model fitted to the
+// measured shape sweep (profiles/r2_packed_shape_sweep.jsonl):
+//     time ~ (P + loops * ceil(n_nodes / L)) * L / throughput(f),   f = pairs * L / resident thread slots,
+// P = 6 node-iterations' worth of per-thread prologue / reduction, loops = 1 (cloud + bands) or 2 (ring and
+// feature loops weigh about as much as the first), throughput(f) = min(1, 1.25 f / (f + 0.25)): half-filled
+// SMs already reach 84 % of the full rate.  ZODI_X2_LANES / ZODI_X2_THREADS force a shape (measurements,
+// tests).
+PackedShape pick_packed_shape(int64_t n, int n_nodes, int n_comps) {
     const char* el = std::getenv("ZODI_X2_LANES");
     const char* et = std::getenv("ZODI_X2_THREADS");
     const int env_lanes = el ? std::atoi(el) : 0, env_threads = et ? std::atoi(et) : 0;
@@ -59,9 +64,16 @@ PackedShape pick_packed_shape(int64_t n, int n_nodes) {
         s.lanes = env_lanes;
         return s;
     }
-    const int64_t pairs = (n + 1) / 2, fill = (int64_t)sm_count() * 1280;
+    const double pairs = 0.5 * (double)(n + 1), slots = (double)sm_count() * 1280.0;
+    const double loops = n_comps == 6 ? 2.0 : 1.0;
+    double best = 0.0;
     s.lanes = 1;
-    while (s.lanes < 8 && pairs * s.lanes < fill && 2 * s.lanes <= n_nodes) s.lanes *= 2;
+    for (int L = 1; L <= 8 && (L == 1 || 2 * L <= 2 * n_nodes); L *= 2) {
+        const double f = pairs * L / slots;
+        const double thr = std::fmin(1.0, 1.25 * f / (f + 0.25));
+        const double cost = (6.0 + loops * ((n_nodes + L - 1) / L)) * L / thr;
+        if (L == 1 || cost < best) { best = cost; s.lanes = L; }
+    }
     return s;
 }
 
@@ -275,7 +287,7 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
         // packed-fp32 kernels: every fp32 evaluation of a Kelsall-family model
         if (precision == ZODI_FP32 && !m->no_x2)
             return launch_kelsall_packed(m->k32, a, m->d_table32, m->d_nodes32,
-                                         pick_packed_shape(a.n, m->k32.n_nodes), stream);
+                                         pick_packed_shape(a.n, m->k32.n_nodes, m->k32.n_comps), stream);
         if (precision == ZODI_FP32) return launch_kelsall_f32(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }

@@ -19,7 +19,7 @@ namespace zodi {
 
 constexpr int kThreads = 256;
 #ifndef ZODI_X2_DEFAULT_THREADS
-#define ZODI_X2_DEFAULT_THREADS 256
+#define ZODI_X2_DEFAULT_THREADS 128
 #endif
 constexpr int kPackedDefaultThreads = ZODI_X2_DEFAULT_THREADS;  // CTA size of the packed kernels
 

@@ -25,7 +25,7 @@ int pick_lanes(int64_t n, int n_nodes);
 
 // Shape of a packed-kernel launch: lanes per PAIR of lines of sight and threads per CTA.
 struct PackedShape { int lanes; int threads; };
-PackedShape pick_packed_shape(int64_t n, int n_nodes);
+PackedShape pick_packed_shape(int64_t n, int n_nodes, int n_comps);
 
 cudaError_t launch_generic_f32(const DevModel<float>& M, const LaunchArgs& a, const Pair<float>* tab,
                                const Pair<float>* nodes, cudaStream_t stream);
