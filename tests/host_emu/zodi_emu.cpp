@@ -114,8 +114,29 @@ static void run_kelsall_x2(const KelsallModel<float>& K, const std::vector<Pair<
     }
 }
 
+// Fused RRM routine (zodi_rrm.cuh).
+template <typename Real>
+static void run_rrm(const RrmModel<Real>& R, const std::vector<Pair<Real>>& tab, const std::vector<Pair<Real>>& nodes,
+                    int64_t n, const double* u, const double* obs, int64_t n_obs, const double* earth,
+                    int64_t n_earth, const uint8_t* flags, int lanes, double* out) {
+    uint32_t mask = 0;
+    for (int c = 0; c < R_NCOMPS; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+        for (int c = 0; c < R_NCOMPS; ++c) out[c * n + j] = 0.0;
+        for (int sub = 0; sub < lanes; ++sub)
+            integrate_rrm<Real>(R, tab.data(), nodes.data(), u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo],
+                                obs[2 * n_obs + jo], earth[je], earth[n_earth + je], mask, sub, lanes,
+                                [&](int ci, Real part) { out[ci * n + j] += (double)part; });
+    }
+}
+
 // fast: 0 generic routine, 1 scalar fused routine, 2 packed fused routines (fp32, no scattering).
-// Returns 1 if the Kelsall fast path was eligible and used, 0 if the generic routine ran.
+// Returns 1 / 2 if the Kelsall fast path was eligible and used, 3 for the fused RRM routine, 0 if the
+// generic routine ran.
 extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, int lanes, int fast,
                                       int64_t n, const double* u, const double* obs, int64_t n_obs,
                                       const double* earth, int64_t n_earth, const uint8_t* flags,
@@ -142,6 +163,26 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
                                       const double* earth, int64_t n_earth, const uint8_t* flags,
                                       double* out) {
     KelsallModel<double> k64;
+    if (fast && d->kind == ZODI_RRM) {
+        DevModel<double> m64;
+        DevModel<float> m32;
+        build_dev_model(*d, m64);
+        narrow_model(m64, m32);
+        RrmModel<double> r64;
+        if (build_rrm_model(*d, m64, r64)) {
+            std::vector<Pair<double>> t64, n64;
+            std::vector<Pair<float>> t32, n32;
+            build_pairs(*d, t64, n64, t32, n32);
+            if (precision == ZODI_FP32) {
+                RrmModel<float> r32;
+                narrow_rrm(r64, m32, r32);
+                run_rrm<float>(r32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+            } else {
+                run_rrm<double>(r64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
+            }
+            return 3;
+        }
+    }
     if (!fast || !build_kelsall_model(*d, k64)) {
         zodi_emu_evaluate(d, precision, lanes, n, u, obs, n_obs, earth, n_earth, flags, out);
         return 0;

@@ -21,7 +21,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emu", "zodi_emu.cpp")
 LIB = os.path.join(HERE, "host_emu", "libzodi_emu.so")
 DEPS = [SRC] + [os.path.join(HERE, "..", "zodipy_b200", "csrc", f)
-                for f in ("zodi_device.cuh", "zodi_model_build.hpp", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh")]
+                for f in ("zodi_device.cuh", "zodi_model_build.hpp", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh",
+                          "zodi_rrm.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -87,6 +88,19 @@ def test_packed_routines_equal_scalar_fused(emu, case_id, lanes):
     # bit-identical on the GPU (ex2.approx.ftz flushes to 0); the host's libm returns denormals
     # where one lane of a pair is beyond the underflow threshold, hence the 1e-37 allowance
     np.testing.assert_allclose(packed, scalar, rtol=0, atol=1e-37)
+
+
+@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("case_id", [c for c in case_ids() if "rrm" in c])
+def test_fused_rrm_routine_matches_reference(emu, case_id, precision, lanes):
+    """Fused RRM routine (zodi_rrm.cuh: grouped bands, shared log2 R^2) against the reference's outputs."""
+    case, a = golden_case(case_id)
+    em, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], precision, lanes, fast=1)
+    assert used == 3, "the shipped RRM layout must take the fused routine"
+    tol, floor = (TOL_FP64, COMP_FLOOR_FP64) if precision == 0 else (TOL_FP32, 1.0)
+    assert max_rel_total(em, a["emission"]) <= tol
+    assert max_rel_comps(em, a["emission"], floor=floor) <= tol
 
 
 @pytest.mark.parametrize("case_id", case_ids())

@@ -32,9 +32,9 @@ def device_model(spec, generic=False, no_x2=False):
 
 
 def test_kernel_selection():
-    """Kelsall-family layouts take the fused kernel; RRM and user-edited layouts the generic one."""
+    """Kelsall-family and RRM layouts take their fused kernels; user-edited layouts the generic one."""
     expect = {"planck18_857": "kelsall", "dirbe_25um_rand": "kelsall", "dirbe_1p25um": "kelsall",
-              "planck13_545": "kelsall", "rrm_60um": "generic", "dirbe_25um_mutated": "generic"}
+              "planck13_545": "kelsall", "rrm_60um": "rrm", "dirbe_25um_mutated": "generic"}
     for case_id, which in expect.items():
         assert device_model(golden_case(case_id)[0]["spec"]).kernel_name == f"zodi_los_{which}_kernel"
     assert device_model(golden_case("planck18_857")[0]["spec"], generic=True).kernel_name == \

@@ -150,6 +150,9 @@ struct zodi_model_s {
     bool kelsall_ok = false;  // model fits the fused Kelsall-family kernel
     KelsallModel<double> k64;
     KelsallModel<float> k32;
+    bool rrm_ok = false;      // model fits the fused RRM kernel
+    RrmModel<double> r64;
+    RrmModel<float> r32;
     // multi-band extension (zodi_multiband_*): this handle then carries band 0 and the shared parts
     int mb_bands = 0;
     MultiBandModel<double> mb64;
@@ -220,6 +223,8 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     narrow_model(m->m64, m->m32);
     m->kelsall_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes &&
                     build_kelsall_model(*d, m->k64);
+    m->rrm_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes && build_rrm_model(*d, m->m64, m->r64);
+    if (m->rrm_ok) narrow_rrm(m->r64, m->m32, m->r32);
     const char* ntp = std::getenv("ZODI_NO_RING_TPOLY");  // testing knob: ring temperature by the power law
     if (m->kelsall_ok && ntp && ntp[0] == '1') m->k64.ring_poly_ok = 0;
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
@@ -290,6 +295,10 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
                                          pick_packed_shape(a.n, m->k32.n_nodes, m->k32.n_comps), stream);
         if (precision == ZODI_FP32) return launch_kelsall_f32(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
+    }
+    if (m->rrm_ok && !m->force_generic) {
+        if (precision == ZODI_FP32) return launch_rrm_f32(m->r32, a, m->d_table32, m->d_nodes32, stream);
+        return launch_rrm_f64(m->r64, a, m->d_table64, m->d_nodes64, stream);
     }
     if (precision == ZODI_FP32) return launch_generic_f32(m->m32, a, m->d_table32, m->d_nodes32, stream);
     return launch_generic_f64(m->m64, a, m->d_table64, m->d_nodes64, stream);
@@ -1064,7 +1073,8 @@ int zodi_number_density(zodi_model_t m, const double* xyz, int64_t n, int64_t xy
 
 const char* zodi_model_kernel_name(zodi_model_t m) {
     if (!m) return "";
-    return (m->kelsall_ok && !m->force_generic) ? "zodi_los_kelsall_kernel" : "zodi_los_generic_kernel";
+    if (m->force_generic) return "zodi_los_generic_kernel";
+    return m->kelsall_ok ? "zodi_los_kelsall_kernel" : (m->rrm_ok ? "zodi_los_rrm_kernel" : "zodi_los_generic_kernel");
 }
 
 int zodi_peer_buffer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle[ZODI_IPC_HANDLE_BYTES]) {
@@ -1113,6 +1123,7 @@ int zodi_peer_buffer_free(int device, void* ptr) {
 
 const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
     if (!m) return "";
+    if (m->rrm_ok && !m->force_generic) return "zodi_los_rrm_kernel";
     if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";
     if (precision == ZODI_FP32 && !m->no_x2) return "zodi_los_kelsall_x2_kernel";
     return "zodi_los_kelsall_kernel";

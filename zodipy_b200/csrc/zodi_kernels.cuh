@@ -14,6 +14,7 @@
 #include "zodi_kelsall.cuh"
 #include "zodi_kelsall_x2.cuh"
 #include "zodi_multiband.cuh"
+#include "zodi_rrm.cuh"
 
 namespace zodi {
 
@@ -306,6 +307,44 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
         if (act0) store_out<float>(args, 0, j0, tot0);
         if (act1) store_out<float>(args, 0, j1, tot1);
     }
+}
+
+// Fused RRM kernel (zodi_rrm.cuh): six node loops for the eight components of the shipped layout.
+// Same thread mapping and staging as the scalar Kelsall kernel.
+template <typename Real, int L>
+__global__ void __launch_bounds__(kThreads)
+zodi_los_rrm_kernel(const __grid_constant__ RrmModel<Real> model,
+                    const __grid_constant__ LaunchArgs args,
+                    const Pair<Real>* __restrict__ g_table,
+                    const Pair<Real>* __restrict__ g_nodes) {
+    __shared__ Pair<Real> s_table[kFastMaxTemps];
+    __shared__ Pair<Real> s_nodes[kFastMaxNodes];
+    for (int i = threadIdx.x; i < model.n_temps; i += blockDim.x) s_table[i] = g_table[i];
+    for (int i = threadIdx.x; i < model.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    if (sizeof(Real) == sizeof(double)) fp64_tables_stage();
+    __syncthreads();
+
+    constexpr int kLosPerCta = kThreads / L;
+    const int sub = threadIdx.x % L;
+    const int64_t j = (int64_t)blockIdx.x * kLosPerCta + threadIdx.x / L;
+    const bool active = j < args.n;
+    const int64_t jj = active ? j : args.n - 1;
+
+    double ux, uy, uz;
+    load_direction(args, jj, ux, uy, uz);
+    double ox, oy, oz, ex, ey;
+    load_positions(args, jj, true, ox, oy, oz, ex, ey);
+
+    Real total = Real(0);
+    integrate_rrm<Real>(
+        model, s_table, s_nodes, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, sub, L,
+        [&](int ci, Real part) {
+            const Real v = lane_group_sum<Real, L>(part);
+            total += v;
+            if (args.return_comps && active && sub == 0)
+                store_out<Real>(args, ci, j, v);
+        });
+    if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
 }
 
 // Multi-band kernel (zodi_multiband.cuh): NB bands of one Kelsall-family model per pass; output

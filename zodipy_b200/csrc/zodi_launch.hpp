@@ -42,5 +42,10 @@ cudaError_t launch_multiband_f32(const MultiBandModel<float>& MB, const LaunchAr
                                  const Pair<float>* nodes, cudaStream_t stream);
 cudaError_t launch_multiband_f64(const MultiBandModel<double>& MB, const LaunchArgs& a, const Pair<double>* tabs,
                                  const Pair<double>* nodes, cudaStream_t stream);
+// fused RRM kernels (zodi_rrm.cuh)
+cudaError_t launch_rrm_f32(const RrmModel<float>& R, const LaunchArgs& a, const Pair<float>* tab,
+                           const Pair<float>* nodes, cudaStream_t stream);
+cudaError_t launch_rrm_f64(const RrmModel<double>& R, const LaunchArgs& a, const Pair<double>* tab,
+                           const Pair<double>* nodes, cudaStream_t stream);
 
 }  // namespace zodi

@@ -9,6 +9,7 @@
 
 #include "zodi_device.cuh"
 #include "zodi_kelsall.cuh"
+#include "zodi_rrm.cuh"
 
 namespace zodi {
 
@@ -325,6 +326,53 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     b.ring_poly_ok = a.ring_poly_ok;
     b.r_dmax = (To)a.r_dmax;
     for (int i = 0; i < kRingPolyTerms; ++i) b.r_tp[i] = (To)a.r_tp[i];
+}
+
+// RRM fast path: returns false unless the model has the shipped rrm-experimental layout (zodi_rrm.cuh):
+// the eight component types in registry order, every component centred on the Sun, the three bands on
+// one range with one temperature law.  M is the generic device form of the same descriptor.
+inline bool build_rrm_model(const zodi_model_desc& d, const DevModel<double>& M, RrmModel<double>& R) {
+    std::memset(&R, 0, sizeof(R));
+    static const int kTypes[R_NCOMPS] = {ZODI_FAN, ZODI_COMET, ZODI_NARROW_BAND, ZODI_NARROW_BAND, ZODI_BROAD_BAND,
+                                         ZODI_INTERSTELLAR, ZODI_RING_RRM, ZODI_FEATURE_RRM};
+    if (d.kind != ZODI_RRM || d.n_comps != R_NCOMPS) return false;
+    const zodi_component_desc* c = d.comps;
+    for (int i = 0; i < R_NCOMPS; ++i) {
+        if (c[i].type != kTypes[i]) return false;
+        if (i != R_INTERSTELLAR && (c[i].x0[0] != 0.0 || c[i].x0[1] != 0.0 || c[i].x0[2] != 0.0)) return false;
+    }
+    for (int b = R_NB_OUT; b <= R_BROAD; ++b)
+        if (c[b].cutoff_inner != c[R_NB_IN].cutoff_inner || c[b].cutoff_outer != c[R_NB_IN].cutoff_outer ||
+            c[b].T_0 != c[R_NB_IN].T_0 || c[b].delta != c[R_NB_IN].delta)
+            return false;
+    R.n_nodes = d.n_nodes; R.n_temps = d.n_temps;
+    const double dt = (d.temps[d.n_temps - 1] - d.temps[0]) / (d.n_temps - 1);
+    R.t_ofs = -d.temps[0] / dt;
+    R.t_top = d.n_temps - 1;
+    R.e1 = d.calibration;
+    for (int i = 0; i < R_NCOMPS; ++i) {
+        R.t_scale[i] = c[i].T_0 / dt;
+        R.mhd[i] = -0.5 * c[i].delta;
+        R.c[i] = M.comps[i];
+    }
+    const DevComp<double>&a = R.c[R_NB_IN], &b = R.c[R_NB_OUT];
+    R.nb_share_plane = (a.nx == b.nx && a.ny == b.ny && a.nz == b.nz);
+    R.f_cos0 = std::cos(c[R_FEATURE].shape[4]);
+    R.f_sin0 = std::sin(c[R_FEATURE].shape[4]);
+    return true;
+}
+
+template <typename To, typename From>
+inline void narrow_rrm(const RrmModel<From>& a, const DevModel<To>& m, RrmModel<To>& b) {
+    std::memset(&b, 0, sizeof(b));
+    b.n_nodes = a.n_nodes; b.n_temps = a.n_temps; b.nb_share_plane = a.nb_share_plane;
+    b.t_ofs = (To)a.t_ofs; b.t_top = (To)a.t_top; b.e1 = (To)a.e1;
+    for (int i = 0; i < R_NCOMPS; ++i) {
+        b.t_scale[i] = (To)a.t_scale[i];
+        b.mhd[i] = (To)a.mhd[i];
+        b.c[i] = m.comps[i];  // already narrowed by narrow_model()
+    }
+    b.f_cos0 = a.f_cos0; b.f_sin0 = a.f_sin0;
 }
 
 // Not-a-knot cubic spline through uniformly or non-uniformly spaced knots, one axis: the same
