@@ -370,7 +370,9 @@ def tod_config(args, torch, zp, engine, oracle, dev, peaks):
     t_host.numpy()[...] += t0
     tk = np.arange(t_host[0].item(), t_host[-1].item() + dt, dt)  # arrange_obstimes
     earth_knots = analytic_earth(tk)
-    eph = engine.DeviceEphemeris(t0, dt, earth_knots, device=dev.index)
+    # np.arange fills t0 + k * delta with delta = (t0 + dt) - t0, not exactly dt: hand the array's own spacing to
+    # the device so that its knot times equal the host's bit for bit (as Model.evaluate does, astro.py)
+    eph = engine.DeviceEphemeris(float(tk[0]), float(tk[1] - tk[0]), earth_knots, device=dev.index)
     # directions: uniform on the sphere, counter-based device RNG (Philox), seed 0
     gen = torch.Generator(device=dev)
     gen.manual_seed(0)

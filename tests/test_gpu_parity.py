@@ -384,7 +384,7 @@ def test_evaluate_lonlat_with_device_ephemeris_and_multiband():
 @pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um"),
                                          ("planck13", 545.0, "GHz"), ("dirbe", 1.25, "um"),
                                          ("dirbe", 3.5, "um")])  # the last two: scattering
-def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
+def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit, monkeypatch):
     """The packed-fp32 kernel (FFMA2, two lines of sight per thread) performs the same operations
     as the scalar fused kernel: results must be bit-identical (incl. ragged tails, per-sample
     observers), and within tolerance of the oracle."""
@@ -407,6 +407,7 @@ def test_packed_kernel_equals_scalar_fused_kernel(name, x, unit):
     assert max_rel_comps(a[:, sel], ref, floor=COMP_FLOOR_FP32) <= TOL_FP32
     # mid-size input: both kernels split the nodes of a line of sight over 8 lanes (same shuffle tree)
     m = 30001
+    monkeypatch.setenv("ZODI_X2_LANES", "8")
     a = packed.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32", return_comps=True)
     b = scalar.evaluate(u[:, :m], obs[:, :m], EARTH_20220114, precision="fp32", return_comps=True)
     np.testing.assert_array_equal(a, b)

@@ -141,6 +141,7 @@ SYMBOLS = {
     "zodi_peer_buffer_open": (C.c_int, [C.c_int, c_uint8_p, C.POINTER(C.c_void_p)]),
     "zodi_peer_buffer_close": (C.c_int, [C.c_int, C.c_void_p]),
     "zodi_peer_buffer_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "zodi_peer_rendezvous": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "zodi_peak_probe": (C.c_int, [C.c_int, C.c_int32, c_double_p]),
     "zodi_kernel_launch_count": (C.c_int64, []),
     "zodi_last_kernel_ms": (C.c_double, [C.c_void_p]),

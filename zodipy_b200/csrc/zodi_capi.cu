@@ -225,8 +225,6 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
                     build_kelsall_model(*d, m->k64);
     m->rrm_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes && build_rrm_model(*d, m->m64, m->r64);
     if (m->rrm_ok) narrow_rrm(m->r64, m->m32, m->r32);
-    const char* ntp = std::getenv("ZODI_NO_RING_TPOLY");  // testing knob: ring temperature by the power law
-    if (m->kelsall_ok && ntp && ntp[0] == '1') m->k64.ring_poly_ok = 0;
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
     const char* fg = std::getenv("ZODI_FORCE_GENERIC");
     m->force_generic = (fg && fg[0] == '1');
@@ -360,9 +358,16 @@ int check_args(const zodi_model_s* m, const zodi_eval_args* a, bool need_u = tru
             return fail(ZODI_ERR_INVALID, "peer output needs ZODI_MEM_DEVICE inputs");
         for (int p = 0; p < a->n_peers; ++p)
             if (!a->peer_out[p]) return fail(ZODI_ERR_INVALID, "peer_out[%d] is NULL", p);
-        if (a->peer_offset < 0 || (a->return_comps && a->cyclic_block == 0 &&
-                                   a->peer_stride < a->peer_offset + a->n))
-            return fail(ZODI_ERR_INVALID, "bad peer_offset/peer_stride");
+        // the kernel stores to peer_offset + g(j), j < n, of every peer's map (row stride peer_stride):
+        // the largest global index must lie inside a row whatever the layout and the number of rows
+        int64_t last = a->n - 1;
+        if (a->cyclic_block > 0 && a->cyclic_parts >= 1) {
+            const int64_t lb = last / a->cyclic_block;
+            last = (lb * a->cyclic_parts + a->cyclic_rank) * a->cyclic_block + (last - lb * a->cyclic_block);
+        }
+        if (a->peer_offset < 0 || a->peer_stride < a->peer_offset + last + 1)
+            return fail(ZODI_ERR_INVALID, "peer slice [%lld, %lld] does not fit a map row of %lld elements",
+                        (long long)a->peer_offset, (long long)(a->peer_offset + last), (long long)a->peer_stride);
     }
     if (a->ephemeris) {
         if (!a->obstime && (a->memory != ZODI_MEM_HOST || !a->ephemeris->d_times || a->ephemeris->n_times != a->n))
@@ -1084,6 +1089,7 @@ int zodi_peer_buffer_alloc(int device, int64_t bytes, void** ptr, uint8_t handle
     if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
     *ptr = nullptr;
     CU_CHECK(cudaMalloc(ptr, (size_t)bytes));
+    CU_CHECK(cudaMemset(*ptr, 0, (size_t)bytes));  // flag arrays rely on it; maps are overwritten anyway
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
     if (e != cudaSuccess) {
@@ -1118,6 +1124,23 @@ int zodi_peer_buffer_free(int device, void* ptr) {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
     CU_CHECK(cudaFree(ptr));
+    return ZODI_OK;
+}
+
+int zodi_peer_rendezvous(int device, void* const* peer_flags, int32_t n_peers, int32_t rank, uint32_t epoch,
+                         void* stream) {
+    if (!peer_flags || n_peers < 1 || n_peers > ZODI_MAX_PEERS || rank < 0 || rank >= n_peers)
+        return fail(ZODI_ERR_INVALID, "bad rendezvous arguments");
+    PeerFlagPtrs f;
+    for (int p = 0; p < ZODI_MAX_PEERS; ++p) {
+        f.p[p] = p < n_peers ? static_cast<uint32_t*>(peer_flags[p]) : nullptr;
+        if (p < n_peers && !f.p[p]) return fail(ZODI_ERR_INVALID, "peer_flags[%d] is NULL", p);
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(ZODI_ERR_CUDA, "cannot select device %d", device);
+    zodi_peer_rendezvous_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_peers, rank, epoch);
+    g_launches.fetch_add(1);
+    CU_CHECK(cudaGetLastError());
     return ZODI_OK;
 }
 

@@ -24,9 +24,6 @@
 
 namespace zodi {
 
-// Ring: table coordinate as a polynomial in d = R_h - R_ring (fp32 kernels), see ring_table_coord().
-constexpr int kRingPolyTerms = 9;
-
 template <typename Real>
 struct KelsallModel {
     int n_comps;   // 4 or 6
@@ -58,10 +55,6 @@ struct KelsallModel {
     // ranges (always double)
     double cutA_in, cutA_out, cutR_in, cutR_out, cutF_in, cutF_out;
     double f_cos0, f_sin0;  // cos / sin of the feature's theta_0 (see feature_rotation)
-    // ring: t(d) = t_scale (R + d)^(-delta) + t_ofs on |d| <= r_dmax as a polynomial (ring_table_coord)
-    int ring_poly_ok;
-    Real r_dmax;
-    Real r_tp[kRingPolyTerms];
 };
 
 // --- table lookup -----------------------------------------------------------------------------
@@ -219,27 +212,6 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
 }
 
 // ---------------- ring (own grid) -------------------------------------------------------------
-// Table coordinate t = t_scale R_h^(-delta) + t_ofs (blackbody.py:30 mapped to knot units) at a ring
-// node.  The ring's density exp(-(d / sigma_r)^2 - ...) with d = R_h - R_ring flushes to exactly 0 in
-// single precision for |d| > r_dmax (0.23 AU for the shipped sigma_r = 0.025 AU), so the fp32 kernels only
-// need t on that window, where it is a degree-8 polynomial in d (Chebyshev fit by the host in double,
-// error < 1e-8 t): 8 FMA-pipe operations instead of MUFU.LG2 + MUFU.EX2 on the XU pipe, which limits
-// these kernels.  Outside the window d is clamped: the value multiplies an exact zero.  The faithful
-// fp64 mode (and fp32 models whose ring is too wide for the fit, ring_poly_ok == 0) keep the power law.
-template <typename Real>
-ZODI_HD Real ring_table_coord(const KelsallModel<Real>& K, Real Rh2, Real d) {
-    using M = Math<Real>;
-    if (sizeof(Real) == sizeof(double) || !K.ring_poly_ok)
-        return M::fma_(K.t_scale, M::exp2_(K.mhd * M::log2_(Rh2)), K.t_ofs);
-    const Real dc = M::min_(M::max_(d, -K.r_dmax), K.r_dmax);
-    Real p = K.r_tp[kRingPolyTerms - 1];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = kRingPolyTerms - 2; k >= 0; --k) p = M::fma_(p, dc, K.r_tp[k]);
-    return p;
-}
-
 // Phi(Theta) / R_h^2 at a node (brightness.py:50-54, scattering.py:29-50); rh_inv = 1 / R_h.
 template <typename Real>
 ZODI_HD Real scatter_term(const KelsallModel<Real>& K, Real ux, Real uy, Real uz, Real xh, Real yh, Real zh,
@@ -263,7 +235,7 @@ ZODI_HD Real kelsall_ring(const KelsallModel<Real>& K, const Pair<Real>* tab, co
         const Real xh = M::fma_(R_los, G.ux, G.ox), yh = M::fma_(R_los, G.uy, G.oy), zh = M::fma_(R_los, G.uz, G.oz);
         const Real Rh2 = M::fma_(xh, xh, M::fma_(yh, yh, zh * zh));
         const Real d = M::sqrt_(Rh2) - K.r_R;
-        const Real B = table_at<Real>(tab, ring_table_coord<Real>(K, Rh2, d), K.t_top);
+        const Real B = table_at<Real>(tab, M::fma_(K.t_scale, M::exp2_(K.mhd * M::log2_(Rh2)), K.t_ofs), K.t_top);
         const Real Zc = M::fma_(xh, K.rnx, M::fma_(yh, K.rny, zh * K.rnz));
         const Real n = M::exp2_neg_(-M::fma_(d * d, K.r_c2, M::abs_(Zc) * K.r_c3));
         aB = M::fma_(nw.b * B, n, aB);

@@ -122,11 +122,9 @@ ZODI_HD TableRef table_ref(const Pair<float>* tab) {
     return r;
 }
 
-// Table lookup for two temperatures (same arithmetic as table_at<float>).  CLAMP = false: the caller
-// guarantees 0 <= t <= t_top (clamping is then the identity).
-template <bool CLAMP = true>
+// Table lookup for two temperatures (same arithmetic as table_at<float>).
 ZODI_HD F2 table_at2(TableRef ref, F2 t, float t_top) {
-    if (CLAMP) t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
+    t = f2(fminf(fmaxf(t.x, 0.0f), t_top), fminf(fmaxf(t.y, 0.0f), t_top));
     const float magic = 12582912.0f;
     const F2 s = add2(add2(t, -0.5f), magic);
     Pair<float> e0, e1;
@@ -308,17 +306,6 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
     emit(0, r0.x, r0.y); emit(1, r1.x, r1.y); emit(2, r2.x, r2.y); emit(3, r3.x, r3.y);
 }
 
-// Polynomial branch of ring_table_coord<float>() for both halves.
-ZODI_HD F2 ring_table_poly2(const KelsallModel<float>& K, F2 d) {
-    const F2 dc = f2(fminf(fmaxf(d.x, -K.r_dmax), K.r_dmax), fminf(fmaxf(d.y, -K.r_dmax), K.r_dmax));
-    F2 p = f2(K.r_tp[kRingPolyTerms - 1]);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = kRingPolyTerms - 2; k >= 0; --k) p = fma2(p, dc, f2(K.r_tp[k]));
-    return p;
-}
-
 // Ring of TWO lines of sight per loop (ring | ring in the two halves of every register pair).  Same
 // operations per line of sight as kelsall_ring<float, SCATTER> (bit-identical results).
 template <bool SCATTER, int L, typename Emit>
@@ -335,9 +322,7 @@ ZODI_HD void kelsall_ring_x2(const KelsallModel<float>& K, const Pair<float>* ta
         const F2 xh = fma2(R_los, ux, ox), yh = fma2(R_los, uy, oy), zh = fma2(R_los, uz, oz);
         const F2 Rh2 = fma2(xh, xh, fma2(yh, yh, mul2(zh, zh)));
         const F2 d = add2(sqrt_2(Rh2), -K.r_R);
-        // polynomial path: t stays inside the table by construction (checked by the host, ring_poly_fit)
-        const F2 B = K.ring_poly_ok ? table_at2<false>(tref, ring_table_poly2(K, d), K.t_top)
-                                    : table_at2(tref, fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs), K.t_top);
+        const F2 B = table_at2(tref, fma2(ex2_2(mul2(lg2_2(Rh2), K.mhd)), K.t_scale, K.t_ofs), K.t_top);
         const F2 Zc = fma2(xh, K.rnx, fma2(yh, K.rny, mul2(zh, K.rnz)));
         const F2 n = ex2_2(fma2(mul2(d, d), K.r_c2, mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), K.r_c3)));
         acc = fma2(mul2(B, nw.b), n, acc);

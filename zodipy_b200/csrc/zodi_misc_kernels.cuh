@@ -118,6 +118,29 @@ __global__ void zodi_max_r2_kernel(const double* __restrict__ obs, int64_t n, in
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
 }
 
+// Completion rendezvous of the fused all-gather (zodi_peer_rendezvous): thread p publishes this rank's
+// epoch to peer p and waits for peer p's epoch in the own array.  Runs behind the integrator kernel on
+// the same stream, so the kernel's peer stores are complete; the system-scope fence + release order
+// them before the flag for the peers' acquire loads.
+struct PeerFlagPtrs { uint32_t* p[ZODI_MAX_PEERS]; };
+__global__ void zodi_peer_rendezvous_kernel(PeerFlagPtrs flags, int n_peers, int rank, uint32_t epoch) {
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[p] + rank), "r"(epoch) : "memory");
+    const uint32_t* mine = flags.p[rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if (clock64() - t0 > (20LL << 30)) {  // ~10 s: a peer died - report instead of hanging the GPU
+            flags.p[rank][ZODI_MAX_PEERS] = 1u;
+            break;
+        }
+    }
+}
+
 // ---- pipe-peak microbenchmarks (roofline denominators measured on the box) -----------------
 template <typename Real>
 __global__ void zodi_peak_fma_kernel(Real* out, int iters) {

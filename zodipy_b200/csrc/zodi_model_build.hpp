@@ -186,42 +186,6 @@ inline void build_pairs(const zodi_model_desc& d, std::vector<Pair<double>>& t64
     }
 }
 
-// Degree-(kRingPolyTerms - 1) polynomial in d for f(d) = t_scale (R0 + d)^(-delta) + t_ofs on |d| <= dmax:
-// Chebyshev interpolation (near-minimax) in x = d / dmax, converted to monomial coefficients in d.
-// Returns the largest absolute error found on a fine grid (knot units).
-inline double ring_poly_fit(double t_scale, double t_ofs, double delta, double R0, double dmax, double* coef) {
-    constexpr int N = kRingPolyTerms;
-    auto f = [&](double d) { return t_scale * std::pow(R0 + d, -delta) + t_ofs; };
-    double c[N];  // Chebyshev coefficients
-    for (int j = 0; j < N; ++j) {
-        double sum = 0.0;
-        for (int k = 0; k < N; ++k) {
-            const double th = kPi * (k + 0.5) / N;
-            sum += f(dmax * std::cos(th)) * std::cos(j * th);
-        }
-        c[j] = sum * (j == 0 ? 1.0 : 2.0) / N;
-    }
-    // T_j(x) -> monomials: T_0 = 1, T_1 = x, T_{j+1} = 2 x T_j - T_{j-1}
-    double mono[N] = {0.0}, Tprev[N] = {0.0}, Tcur[N] = {0.0}, Tnext[N];
-    Tprev[0] = 1.0;
-    Tcur[1] = 1.0;
-    for (int i = 0; i < N; ++i) mono[i] = c[0] * Tprev[i] + (N > 1 ? c[1] * Tcur[i] : 0.0);
-    for (int j = 2; j < N; ++j) {
-        for (int i = 0; i < N; ++i) Tnext[i] = (i > 0 ? 2.0 * Tcur[i - 1] : 0.0) - Tprev[i];
-        for (int i = 0; i < N; ++i) { mono[i] += c[j] * Tnext[i]; Tprev[i] = Tcur[i]; Tcur[i] = Tnext[i]; }
-    }
-    double scale = 1.0;
-    for (int i = 0; i < N; ++i) { coef[i] = mono[i] * scale; scale /= dmax; }
-    double worst = 0.0;
-    for (int k = 0; k <= 400; ++k) {
-        const double d = dmax * (-1.0 + k / 200.0);
-        double p = coef[N - 1];
-        for (int i = N - 2; i >= 0; --i) p = p * d + coef[i];
-        worst = std::fmax(worst, std::fabs(p - f(d)));
-    }
-    return worst;
-}
-
 // Kelsall-family fast path: returns false if the model does not have the layout the fused
 // kernel assumes (then the generic kernel is used).  See zodi_kelsall.cuh.
 inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& K) {
@@ -283,17 +247,6 @@ inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& 
         K.rnx = r.sin_Omega * r.sin_i; K.rny = -r.cos_Omega * r.sin_i; K.rnz = r.cos_i;
         K.r_R = r.shape[1]; K.r_c2 = -kLog2e / (r.shape[2] * r.shape[2]); K.r_c3 = -kLog2e / r.shape[3];
         K.cutR_in = r.cutoff_inner; K.cutR_out = r.cutoff_outer;
-        // beyond |d| = r_dmax the exponent -(d / sigma_r)^2 log2e is below -127: ex2.approx.ftz returns 0
-        K.r_dmax = std::sqrt(127.0 / kLog2e) * std::fabs(r.shape[2]) * 1.001;
-        K.ring_poly_ok = 0;
-        if (K.r_dmax < 0.5 * K.r_R) {
-            const double err = ring_poly_fit(K.t_scale, K.t_ofs, d.delta, K.r_R, K.r_dmax, K.r_tp);
-            // the packed kernels skip the table clamps on this path: the window must map inside the table
-            const double t_lo = K.t_scale * std::pow(K.r_R + K.r_dmax, -d.delta) + K.t_ofs;
-            const double t_hi = K.t_scale * std::pow(K.r_R - K.r_dmax, -d.delta) + K.t_ofs;
-            K.ring_poly_ok = err <= 2e-8 * (std::fabs(K.t_scale) + std::fabs(K.t_ofs)) &&
-                             std::fmin(t_lo, t_hi) > 0.5 && std::fmax(t_lo, t_hi) < K.t_top - 0.5;
-        }
         const zodi_component_desc& f = c[5];  // n_0, R, sigma_r, sigma_z, theta_rad, sigma_theta_rad
         K.fnx = f.sin_Omega * f.sin_i; K.fny = -f.cos_Omega * f.sin_i; K.fnz = f.cos_i;
         K.f_R = f.shape[1]; K.f_c2 = -kLog2e / (f.shape[2] * f.shape[2]); K.f_c3 = -kLog2e / f.shape[3];
@@ -323,9 +276,6 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     b.cutA_in = a.cutA_in; b.cutA_out = a.cutA_out; b.cutR_in = a.cutR_in; b.cutR_out = a.cutR_out;
     b.cutF_in = a.cutF_in; b.cutF_out = a.cutF_out;
     b.f_cos0 = a.f_cos0; b.f_sin0 = a.f_sin0;
-    b.ring_poly_ok = a.ring_poly_ok;
-    b.r_dmax = (To)a.r_dmax;
-    for (int i = 0; i < kRingPolyTerms; ++i) b.r_tp[i] = (To)a.r_tp[i];
 }
 
 // RRM fast path: returns false unless the model has the shipped rrm-experimental layout (zodi_rrm.cuh):

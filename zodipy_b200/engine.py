@@ -194,7 +194,8 @@ class DeviceModel:
         self._lib = _cabi.load()
         self.spec = spec
         self.device = int(device)
-        self.ncomps = len(spec["comps"])
+        self.ncomps = len(spec["comps"])          # rows of a return_comps output
+        self.n_model_comps = len(spec["comps"])   # components of the model (rows of outside_flags)
         self._handle = C.c_void_p()
         desc, keep = pack_desc(spec)
         _cabi.check(self._lib.zodi_model_create(C.byref(desc), self.device, C.byref(self._handle)))
@@ -205,7 +206,7 @@ class DeviceModel:
         desc, keep = pack_desc(spec)
         _cabi.check(self._lib.zodi_model_update(self._handle, C.byref(desc)))
         self.spec = spec
-        self.ncomps = len(spec["comps"])
+        self.ncomps = self.n_model_comps = len(spec["comps"])
         del keep
 
     def close(self) -> None:
@@ -318,8 +319,8 @@ class DeviceModel:
             stream = None
         if n == 0:
             return out
-        if peer_map is not None and peer_map.cyclic is None and peer_map.offset + n > peer_map.n_total:
-            raise ValueError("slice does not fit the peer map")
+        if peer_map is not None:
+            self._check_peer_slice(peer_map, n)
 
         if outside_flags is None:
             if device_mem and n_obs == 1:
@@ -329,9 +330,7 @@ class DeviceModel:
             else:
                 flags = self.outside_flags(obs_a)
         else:
-            flags = np.ascontiguousarray(outside_flags, dtype=np.uint8)
-            if flags.shape != (self.ncomps, 2):
-                raise ValueError(f"outside_flags must have shape ({self.ncomps}, 2)")
+            flags = self._checked_flags(outside_flags)
 
         args = _cabi.EvalArgs()
         args.n = n
@@ -354,6 +353,27 @@ class DeviceModel:
                 args.cyclic_block, args.cyclic_parts, args.cyclic_rank = peer_map.cyclic
         self._dispatch(args, lonlat)
         return out
+
+    def _checked_flags(self, outside_flags) -> np.ndarray:
+        """(n_model_comps, 2) uint8 early-out flags: the library reads 2 bytes per MODEL component, whatever
+        the number of output rows (a multi-band handle returns one row per band)."""
+        flags = np.ascontiguousarray(outside_flags, dtype=np.uint8)
+        if flags.shape != (self.n_model_comps, 2):
+            raise ValueError(f"outside_flags must have shape ({self.n_model_comps}, 2)")
+        return flags
+
+    def _check_peer_slice(self, peer_map, n: int) -> None:
+        """The slice this call stores must lie inside every peer's map (the kernel writes remote memory)."""
+        if peer_map.cyclic is None:
+            if peer_map.offset < 0 or peer_map.offset + n > peer_map.n_total:
+                raise ValueError("slice does not fit the peer map")
+            return
+        from .sharding import cyclic_count
+
+        block, parts, rank = peer_map.cyclic
+        if n != cyclic_count(peer_map.n_total - peer_map.offset, parts, rank, block):
+            raise ValueError("block-cyclic shard does not match the peer map: this rank must evaluate exactly its "
+                             f"share of the {peer_map.n_total - peer_map.offset} mapped lines of sight")
 
     def _dispatch(self, args, lonlat) -> None:
         if lonlat is None:
@@ -403,8 +423,7 @@ class DeviceModel:
         if n == 0:
             return out
         r_max = ephemeris.prepare(t_a, observer)
-        flags = spec_outside_flags(self.spec, r_max) if outside_flags is None else \
-            np.ascontiguousarray(outside_flags, dtype=np.uint8)
+        flags = spec_outside_flags(self.spec, r_max) if outside_flags is None else self._checked_flags(outside_flags)
         args = _cabi.EvalArgs()
         args.n = n
         args.u, args.u_stride = u_ptr, u_stride
@@ -482,6 +501,10 @@ class DeviceModel:
             out_ptr = out.ctypes.data
         if n == 0:
             return out
+        if peer_map is not None:
+            if peer_map.cyclic is not None and hi - lo != peer_map.n_total - peer_map.offset:
+                raise ValueError("with a block-cyclic peer map pix_range must span exactly the mapped pixels")
+            self._check_peer_slice(peer_map, n)
         flags = spec_outside_flags(self.spec, float(np.sqrt((obs_h ** 2).sum())))
         h = _cabi.HealpixArgs()
         a = h.base
@@ -654,6 +677,7 @@ class DeviceMultiBand(DeviceModel):
         self.device = int(device)
         self.n_bands = len(specs)
         self.ncomps = self.n_bands  # rows of the output
+        self.n_model_comps = len(specs[0]["comps"])  # rows of outside_flags
         descs = (_cabi.ModelDesc * self.n_bands)()
         keep = []
         for i, sp in enumerate(specs):

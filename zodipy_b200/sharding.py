@@ -131,13 +131,24 @@ def evaluate_sharded(evaluate_fn, max_radius_fn, flags_fn, u_local, obs_local, e
 class PeerMap:
     """Full-map output buffers of all ranks, mapped into this process (CUDA IPC over NVLink).
 
-    Every rank allocates one (rows, n_total) buffer with the library (plain ``cudaMalloc`` so
-    that it can be exported), the IPC handles are exchanged once with ``all_gather_object``, and
-    each rank maps every peer's buffer.  ``DeviceModel.evaluate(..., peer_map=pm)`` then makes the
-    compute kernel store this rank's slice into all of them (fused all-gather); ``finish()``
-    is the stream-ordered rendezvous after which ``pm.tensor`` holds the complete map on every
-    rank.  One process per GPU, ranks of one NVSwitch box.
+    Every rank allocates TWO (rows, n_total) buffers with the library (plain ``cudaMalloc`` so that they
+    can be exported) plus a small flag array, the IPC handles are exchanged once with
+    ``all_gather_object``, and each rank maps every peer's buffers.
+    ``DeviceModel.evaluate(..., peer_map=pm)`` makes the compute kernel store this rank's slice into
+    the current buffer of ALL ranks (fused all-gather); ``finish()`` enqueues the completion rendezvous
+    (one tiny kernel, ``zodi_peer_rendezvous``: publish this rank's epoch to every peer, wait for
+    theirs) behind it and returns the assembled map, valid in stream order on every rank.
+
+    Double buffering closes the write-after-read hazard of repeated evaluations: evaluation i + 1
+    writes the OTHER buffer, and evaluation i + 2 - which reuses the buffer of evaluation i - can only
+    start on any rank after that rank passed rendezvous i + 1, i.e. after every peer launched its
+    kernel i + 1, which is stream-ordered behind that peer's reads of map i.  So: read the returned map
+    on the stream that calls ``evaluate`` (or make that stream wait for the reader) and it is safe to
+    keep evaluating while peers are still reading the previous map.  One process per GPU, ranks of one
+    NVSwitch box.
     """
+
+    N_BUFFERS = 2
 
     def __init__(self, n_total: int, rows: int, dtype, device_index: int, group=None,
                  cyclic_block: int = 0):
@@ -156,43 +167,82 @@ class PeerMap:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > _cabi.MAX_PEERS:
             raise ValueError(f"at most {_cabi.MAX_PEERS} peers")
+        self.world, self.rank = world, rank
         # contiguous np.array_split shards by default; block-cyclic (load-balanced) on request
         self.cyclic = (int(cyclic_block), world, rank) if cyclic_block else None
         self.offset = 0 if self.cyclic else split_bounds(self.n_total, world)[rank][0]
         nbytes = self.rows * self.n_total * self.dtype.itemsize
-        own = C.c_void_p()
-        handle = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES)()
-        _cabi.check(self._lib.zodi_peer_buffer_alloc(self.device_index, nbytes, C.byref(own), handle))
-        self._own = own.value
+        sizes = [nbytes] * self.N_BUFFERS + [4 * (_cabi.MAX_PEERS + 1)]  # maps + flag array (zeroed by alloc)
+        self._own, mine = [], []
+        for size in sizes:
+            own = C.c_void_p()
+            handle = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES)()
+            _cabi.check(self._lib.zodi_peer_buffer_alloc(self.device_index, size, C.byref(own), handle))
+            self._own.append(own.value)
+            mine.append(bytes(handle))
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self.pointers, self._opened = [], []
-        for r, h in enumerate(handles):
-            if r == rank:
-                self.pointers.append(self._own)
-                continue
-            buf = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES).from_buffer_copy(h)
-            ptr = C.c_void_p()
-            _cabi.check(self._lib.zodi_peer_buffer_open(self.device_index, buf, C.byref(ptr)))
-            self.pointers.append(ptr.value)
-            self._opened.append(ptr.value)
-        # torch view of the OWN buffer (no copy)
+        dist.all_gather_object(handles, mine, group=group)
+        self._opened = []
+        mapped = [[] for _ in sizes]  # [buffer][rank] -> pointer in this process
+        for r, hs in enumerate(handles):
+            for b, h in enumerate(hs):
+                if r == rank:
+                    mapped[b].append(self._own[b])
+                    continue
+                buf = (C.c_uint8 * _cabi.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                ptr = C.c_void_p()
+                _cabi.check(self._lib.zodi_peer_buffer_open(self.device_index, buf, C.byref(ptr)))
+                mapped[b].append(ptr.value)
+                self._opened.append(ptr.value)
+        self._map_pointers = mapped[:self.N_BUFFERS]
+        self._flag_pointers = (C.c_void_p * world)(*mapped[self.N_BUFFERS])
+        # torch views of the OWN buffers (no copy)
         tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
         shape = (self.rows, self.n_total) if self.rows > 1 else (self.n_total,)
-        iface = {"shape": shape, "typestr": "<f4" if self.dtype == np.float32 else "<f8",
-                 "data": (self._own, False), "version": 2}
-        holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
-        self.tensor = torch.as_tensor(holder, device=torch.device("cuda", self.device_index))
-        assert self.tensor.dtype == tdtype and self.tensor.data_ptr() == self._own
-        self._token = torch.zeros(1, dtype=torch.float32, device=self.tensor.device)
+        self._views = []
+        for b in range(self.N_BUFFERS):
+            iface = {"shape": shape, "typestr": "<f4" if self.dtype == np.float32 else "<f8",
+                     "data": (self._own[b], False), "version": 2}
+            holder = type("_Buf", (), {"__cuda_array_interface__": iface})()
+            view = torch.as_tensor(holder, device=torch.device("cuda", self.device_index))
+            assert view.dtype == tdtype and view.data_ptr() == self._own[b]
+            self._views.append(view)
+        flag_iface = {"shape": (_cabi.MAX_PEERS + 1,), "typestr": "<i4", "data": (self._own[-1], False), "version": 2}
+        self._flags_view = torch.as_tensor(type("_Buf", (), {"__cuda_array_interface__": flag_iface})(),
+                                           device=torch.device("cuda", self.device_index))
+        self._cur = 0      # buffer the next evaluation writes
+        self._epoch = 0
+        self.tensor = self._views[0]
+        # every rank must have mapped (and the owner zeroed) the flag arrays before the first rendezvous
+        torch.cuda.synchronize(self.device_index)
+        dist.barrier(group=group)
+
+    @property
+    def pointers(self):
+        """Every rank's CURRENT map buffer as mapped in this process (the kernel's peer_out[])."""
+        return self._map_pointers[self._cur]
 
     def finish(self):
-        """Stream-ordered rendezvous: returns once every rank's kernel (and therefore all of its
-        peer stores) has completed.  A 4-byte NCCL all-reduce enqueued behind the kernel."""
-        import torch.distributed as dist
+        """Stream-ordered completion: enqueues the rendezvous kernel behind the integrator kernel and
+        returns this rank's assembled map (valid for work enqueued on the same stream afterwards).  The
+        next evaluation writes the other buffer."""
+        import torch
 
-        dist.all_reduce(self._token, group=self.group)
+        self._epoch += 1
+        stream = torch.cuda.current_stream(self.device_index).cuda_stream
+        from . import _cabi
+
+        _cabi.check(self._lib.zodi_peer_rendezvous(self.device_index, self._flag_pointers, self.world, self.rank,
+                                                   self._epoch & 0xFFFFFFFF, stream))
+        self.tensor = self._views[self._cur]
+        self._cur = (self._cur + 1) % self.N_BUFFERS
         return self.tensor
+
+    def timed_out(self) -> bool:
+        """True if a rendezvous gave up waiting for a peer (synchronises the device)."""
+        from . import _cabi
+
+        return bool(self._flags_view[_cabi.MAX_PEERS].item())
 
     def close(self):
         import torch
@@ -203,5 +253,8 @@ class PeerMap:
         self._opened = []
         if self._own:
             self.tensor = None
-            self._lib.zodi_peer_buffer_free(self.device_index, self._own)
-            self._own = None
+            self._views = []
+            self._flags_view = None
+            for ptr in self._own:
+                self._lib.zodi_peer_buffer_free(self.device_index, ptr)
+            self._own = []
