@@ -57,6 +57,19 @@ def _worker(rank, world, port, backend, case_id, per_sample, precision, use_peer
             dm.evaluate(u, obs, earth, return_comps=True, precision=precision,
                         outside_flags=sharding_flags(dm, r_glob), peer_map=pm)
             result["fused"] = pm.finish().cpu().numpy()
+            # repeated evaluations into ONE PeerMap with different inputs and no barrier in between: the
+            # double-buffered maps + the per-evaluation rendezvous must keep every map intact while peers
+            # are already storing the next one (write-after-read hazard of a single-buffered map)
+            maps = []
+            for scale in WAR_SCALES[:2]:
+                dm.evaluate(u, obs * scale, earth, return_comps=True, precision=precision,
+                            outside_flags=sharding_flags(dm, r_glob * scale), peer_map=pm)
+                maps.append(pm.finish())
+            result["war"] = [m.cpu().numpy() for m in maps]  # read only now: evaluation 2 is already in flight
+            dm.evaluate(u, obs * WAR_SCALES[2], earth, return_comps=True, precision=precision,
+                        outside_flags=sharding_flags(dm, r_glob * WAR_SCALES[2]), peer_map=pm)  # reuses buffer 1
+            result["war"].append(pm.finish().cpu().numpy())
+            assert not pm.timed_out()
             dist.barrier()
             pm.close()
         if use_peer_map:
@@ -84,6 +97,9 @@ def _worker(rank, world, port, backend, case_id, per_sample, precision, use_peer
         raise
     finally:
         dist.destroy_process_group()
+
+
+WAR_SCALES = (1.001, 0.999, 1.002)  # observer scalings of the repeated evaluations (stay inside every cutoff)
 
 
 def sharding_flags(dm, r_max):
@@ -136,11 +152,17 @@ def test_fused_peer_store_equals_allgather(case_id, per_sample):
     case, a = golden_case(case_id)
     single = engine.DeviceModel(case["spec"], 0).evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
     results = _run(world, "nccl", case_id, per_sample, "fp64", True)
+    dm1 = engine.DeviceModel(case["spec"], 0)
+    singles_scaled = [dm1.evaluate(a["u"], a["obs"] * s, a["earth"], return_comps=True,
+                                   outside_flags=sharding_flags(dm1, dm1.max_observer_radius(a["obs"]) * s))
+                      for s in WAR_SCALES]
     hp_single = engine.DeviceModel(case["spec"], 0).evaluate_healpix(
         16, a["obs"][:, :1], a["earth"][:, :1], return_comps=True)
     for r in range(world):
         np.testing.assert_array_equal(results[r]["gathered"], single)
         np.testing.assert_array_equal(results[r]["fused"], single)
+        for k, scale in enumerate(WAR_SCALES):
+            np.testing.assert_array_equal(results[r]["war"][k], singles_scaled[k])
         np.testing.assert_array_equal(results[r]["cyclic_healpix"], hp_single)
         # directions from the host pix2vec differ from the device routine in the last ulp
         np.testing.assert_allclose(results[r]["cyclic_array"], hp_single, rtol=1e-12)

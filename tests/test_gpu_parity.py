@@ -650,3 +650,97 @@ def test_multiband_rejects_unsupported():
         zp.MultiBandModel([zp.Quantity(25.0, "um")] * 17).device_model
     with pytest.raises(ValueError):
         zp.MultiBandModel([zp.Quantity(25.0, "um")], weights=[None, None])
+
+
+def _year_ephemeris_inputs(n, seed=0):
+    """BASELINE config 4 at reduced size: samples spread uniformly over one year (t_i = t0 + i * 365.25 / n),
+    hourly knots on np.arange's grid, uniform random pointings."""
+    t0, dt = 59215.0, 1.0 / 24.0
+    t = t0 + np.arange(n, dtype=np.float64) * (365.25 / n)
+    tk = np.arange(t[0], t[-1] + dt, dt)  # arrange_obstimes (zodipy/bodies.py:16-19)
+    lon = 2 * np.pi * (tk - t0) / 365.25 + 1.7
+    r = 1.0 - 0.0167 * np.cos(lon - 1.8)
+    earth_knots = np.array([r * np.cos(lon), r * np.sin(lon), 1e-5 * np.sin(3 * lon)])
+    rng = np.random.default_rng(seed)
+    u = rng.normal(size=(3, n))
+    u /= np.linalg.norm(u, axis=0)
+    return tk, earth_knots, t, np.ascontiguousarray(u)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_tod_one_year_semb_l2_device_ephemeris(precision):
+    """BASELINE config 4's path at 1e6 samples: per-sample obstimes over one year, hourly knots -> device
+    spline, observer = semb-l2 with the reference's whole-array norm (zodipy/bodies.py:38-50), against the
+    oracle fed with scipy CubicSpline positions on the host; host-memory and device-memory entries agree."""
+    import torch
+    from scipy.interpolate import CubicSpline
+
+    n = 1_000_000
+    tk, earth_knots, t, u = _year_ephemeris_inputs(n)
+    model = zp.Model(zp.Quantity(25.0, "um"), precision=precision)
+    eph = model.ephemeris(float(tk[0]), float(tk[1] - tk[0]), earth_knots)
+    got = model.evaluate_tod_xyz(u, t, eph, observer="semb-l2")
+    earth = CubicSpline(tk, earth_knots, axis=-1)(t)
+    norm = np.linalg.norm(earth)  # un-axised: Frobenius norm of the (3, n) array
+    scale = (norm + engine.MEAN_DIST_TO_L2) / norm
+    sel = np.sort(np.random.default_rng(1).choice(n, 3000, replace=False))
+    ref = oracle.evaluate(model.spec, u[:, sel], scale * earth[:, sel], earth[:, sel]).sum(axis=0)
+    tol = TOL_FP64 if precision == "fp64" else TOL_FP32
+    assert np.max(np.abs(got[sel] - ref) / np.abs(ref)) <= tol
+    dev = torch.device("cuda:0")
+    got_dev = model.evaluate_tod_xyz(torch.as_tensor(u, device=dev), torch.as_tensor(t, device=dev), eph,
+                                     observer="semb-l2")
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), got)
+    lon, lat = np.arctan2(u[1], u[0]), np.arcsin(np.clip(u[2], -1, 1))
+    got_ll = model.evaluate_lonlat(lon, lat, ephemeris=eph, obstime=t, observer="semb-l2")
+    np.testing.assert_allclose(got_ll, got, rtol=1e-12 if precision == "fp64" else 3e-6)
+
+
+@pytest.mark.parametrize("observer", ["earth", "semb-l2"])
+def test_multi_device_tod_and_healpix_bitwise(observer, monkeypatch):
+    """Model(devices=[...]): time-ordered data with on-device ephemerides split over several handles (global
+    semb-l2 norm and early-out flags combined on the host) and HEALPix maps split by pixel range are
+    bit-identical to one handle."""
+    import torch
+
+    monkeypatch.setattr(engine.MultiDeviceModel, "MIN_LOS_PER_DEVICE", 1)
+    devices = [i % torch.cuda.device_count() for i in range(3)]
+    one = zp.Model(zp.Quantity(25.0, "um"), precision="fp32", device=0)
+    many = zp.Model(zp.Quantity(25.0, "um"), precision="fp32", devices=devices)
+    n = 200_003
+    tk, earth_knots, t, u = _year_ephemeris_inputs(n, seed=5)
+    eph1 = one.ephemeris(float(tk[0]), float(tk[1] - tk[0]), earth_knots)
+    ephn = many.ephemeris(float(tk[0]), float(tk[1] - tk[0]), earth_knots)
+    assert hasattr(ephn, "parts") and len(ephn.parts) == 3
+    ref = one.evaluate_tod_xyz(u, t, eph1, observer=observer, return_comps=True)
+    got = many.evaluate_tod_xyz(u, t, ephn, observer=observer, return_comps=True)
+    if observer == "earth":
+        np.testing.assert_array_equal(got, ref)
+    else:  # the global sum |earth|^2 is added in another order: scale equal to ~1 ulp
+        np.testing.assert_allclose(got, ref, rtol=2e-6)
+    lon, lat = np.arctan2(u[1], u[0]), np.arcsin(np.clip(u[2], -1, 1))
+    np.testing.assert_allclose(many.evaluate_lonlat(lon, lat, ephemeris=ephn, obstime=t, observer=observer),
+                               one.evaluate_lonlat(lon, lat, ephemeris=eph1, obstime=t, observer=observer), rtol=2e-6)
+    for kwargs in ({}, {"return_comps": True}, {"pix_range": (1000, 150_001), "nest": True}):
+        np.testing.assert_array_equal(many.evaluate_healpix(128, EARTH_20220114, out_dtype=np.float32, **kwargs),
+                                      one.evaluate_healpix(128, EARTH_20220114, out_dtype=np.float32, **kwargs))
+
+
+def test_nprocesses_maps_to_devices(monkeypatch):
+    """Model.evaluate(..., nprocesses=k) -> min(k, visible GPUs) devices when the placement was left to the
+    library (zodipy/model.py:182-198: k workers); explicit device= / devices= and LOCAL_RANK are respected."""
+    import torch
+
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    auto = zp.Model(zp.Quantity(25.0, "um"))
+    auto._use_processes(1)
+    assert auto._devices == [0]
+    auto._use_processes(64)
+    assert auto._devices == list(range(torch.cuda.device_count()))
+    pinned = zp.Model(zp.Quantity(25.0, "um"), device=0)
+    pinned._use_processes(64)
+    assert pinned._devices == [0]
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    ranked = zp.Model(zp.Quantity(25.0, "um"))
+    ranked._use_processes(64)
+    assert ranked._devices == [0]

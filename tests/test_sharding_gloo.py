@@ -168,3 +168,94 @@ def test_single_process_multi_device_host_sharding(monkeypatch, n_devices, case_
     calls.clear()
     np.testing.assert_array_equal(multi.evaluate(a["u"], a["obs"], a["earth"], return_comps=True), a["emission"])
     assert [c[0] for c in calls] == [0]
+
+
+@pytest.mark.parametrize("observer", ["earth", "semb-l2"])
+def test_single_process_multi_device_tod_and_healpix(monkeypatch, observer):
+    """MultiDeviceModel.evaluate_tod: the reductions over ALL samples (semb-l2 whole-array norm, quirk Q5;
+    global early-out flags, quirk Q1) are combined on the host before any device integrates, every shard
+    then uses the global observer scale - equal to the unsharded evaluation.  evaluate_healpix: pixel
+    ranges split by the array_split rule, results in place.  Per-device compute is stubbed by the oracle
+    (host CubicSpline positions)."""
+    from scipy.interpolate import CubicSpline
+
+    from zodipy_b200 import engine, healpix
+
+    case, _ = golden_case("dirbe_25um_rand")
+    spec = case["spec"]
+    t0, dt, n_knots = 59215.0, 1.0 / 24.0, 60 * 24
+    tk = t0 + dt * np.arange(n_knots)
+    lon_e = 2 * np.pi * (tk - t0) / 365.25 + 1.7
+    earth_knots = (1.0 - 0.0167 * np.cos(lon_e - 1.8)) * np.array([np.cos(lon_e), np.sin(lon_e), 1e-5 * np.sin(3 * lon_e)])
+    spline = CubicSpline(tk, earth_knots, axis=-1)
+
+    class StubEphemeris:
+        def __init__(self, t0_, dt_, earth_knots_, obs_knots_=None, device=0):
+            self.device, self.scale, self.staged = device, 1.0, None
+
+        def set_obs_scale(self, s):
+            self.scale = float(s)
+
+        def stats(self, t):
+            e = spline(np.asarray(t))
+            r2 = (e * e).sum(axis=0)
+            self.staged = np.array(t)
+            return float(r2.sum()), float(np.sqrt(r2.max())), self.scale * float(np.sqrt(r2.max()))
+
+        def close(self):
+            pass
+
+    class StubDeviceModel:
+        def __init__(self, spec_, device):
+            self.spec, self.device, self.ncomps = spec_, device, len(spec_["comps"])
+            self._eval = _oracle_with_flags(spec_)
+
+        def evaluate(self, u, obs=None, earth=None, *, ephemeris=None, obstime=None, observer="earth", lonlat=None,
+                     return_comps=False, precision="fp64", out=None, out_dtype=None, outside_flags=None):
+            assert observer == "prepared" and np.array_equal(ephemeris.staged, obstime)  # stats ran on THIS shard
+            if lonlat is not None:
+                u = np.array([np.cos(lonlat.lat) * np.cos(lonlat.lon), np.cos(lonlat.lat) * np.sin(lonlat.lon),
+                              np.sin(lonlat.lat)])
+            e = spline(obstime)
+            out[...] = self._eval(u, ephemeris.scale * e, e, outside_flags, return_comps).numpy()
+
+        def evaluate_healpix(self, nside, obs, earth=None, *, pix_range, rot, nest, return_comps, precision, out,
+                             out_dtype):
+            u = healpix.pix2vec_ring(nside, np.arange(*pix_range))
+            flags = spec_outside_flags(self.spec, float(np.sqrt((np.asarray(obs) ** 2).sum())))
+            out[...] = self._eval(u, np.asarray(obs).reshape(3, 1), np.asarray(obs if earth is None else earth).reshape(3, 1),
+                                  flags, return_comps).numpy()
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(engine, "DeviceModel", StubDeviceModel)
+    monkeypatch.setattr(engine, "DeviceEphemeris", StubEphemeris)
+    monkeypatch.setattr(engine.MultiDeviceModel, "MIN_LOS_PER_DEVICE", 1)
+    multi = engine.MultiDeviceModel(spec, [0, 1, 2])
+    rng = np.random.default_rng(3)
+    n = 301
+    t = np.sort(rng.uniform(tk[0], tk[-1], n))
+    u = rng.normal(size=(3, n))
+    u /= np.linalg.norm(u, axis=0)
+    eph = multi.ephemeris(t0, dt, earth_knots)
+    got = multi.evaluate_tod(u, t, eph, observer=observer, return_comps=True)
+    earth = spline(t)
+    norm = np.linalg.norm(earth)  # un-axised: the whole (3, n) array (zodipy/bodies.py:47)
+    scale = (norm + engine.MEAN_DIST_TO_L2) / norm if observer == "semb-l2" else 1.0
+    ref = oracle.evaluate(spec, u, scale * earth, earth)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-300)
+    lon, lat = np.arctan2(u[1], u[0]), np.arcsin(np.clip(u[2], -1, 1))
+    got_ll = multi.evaluate_tod(None, t, eph, observer=observer, lonlat=(lon, lat))
+    np.testing.assert_allclose(got_ll, ref.sum(axis=0), rtol=1e-9)
+    with pytest.raises(ValueError):
+        multi.evaluate_tod(u, t[:-1], eph)
+    # HEALPix map split over the devices
+    nside = 4
+    obs = np.array([-0.39, 0.90, 0.0])
+    hp = multi.evaluate_healpix(nside, obs, return_comps=True)
+    ref_hp = oracle.evaluate(spec, healpix.pix2vec_ring(nside, np.arange(12 * nside * nside)), obs.reshape(3, 1),
+                             obs.reshape(3, 1))
+    np.testing.assert_array_equal(hp, ref_hp)
+    part = multi.evaluate_healpix(nside, obs, pix_range=(10, 77))
+    np.testing.assert_array_equal(part, ref_hp.sum(axis=0)[10:77])

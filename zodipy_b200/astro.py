@@ -142,7 +142,7 @@ def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device, with_
     ``CubicSpline(...)(obstimes)`` on the host.  Returns (ephemeris, observer_mode, ecliptic unit
     vectors, sample times in MJD).
     """
-    from .engine import DeviceEphemeris
+    from .engine import DeviceEphemeris, MultiDeviceEphemeris
 
     knots_mjd = interp_obstimes.mjd
     earth_knots = _body_xyz("earth", interp_obstimes, ephemeris)
@@ -157,6 +157,10 @@ def device_ephemeris(skycoord, obspos, interp_obstimes, ephemeris, device, with_
     # np.arange(t0, t1 + dt, dt) fills t0 + k * delta with delta = (t0 + dt) - t0 (NOT exactly dt):
     # use the array's own spacing so the device knots equal the reference's knot times bit for bit
     delta = float(knots_mjd[1] - knots_mjd[0])
-    eph = DeviceEphemeris(float(knots_mjd[0]), delta, earth_knots, obs_knots, device=device)
+    devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+    if len(devices) > 1:
+        eph = MultiDeviceEphemeris(float(knots_mjd[0]), delta, earth_knots, obs_knots, devices)
+    else:
+        eph = DeviceEphemeris(float(knots_mjd[0]), delta, earth_knots, obs_knots, device=devices[0])
     u_xyz = sky_unit_vectors(skycoord) if with_directions else None
     return eph, mode, u_xyz, np.ascontiguousarray(skycoord.obstime.mjd, dtype=np.float64)

@@ -394,6 +394,9 @@ class DeviceModel:
 
     def _evaluate_tod(self, u_a, u_ptr, n, u_stride, device_mem, ephemeris, obstime, observer,
                       return_comps, precision, out, out_dtype, outside_flags, lonlat=None):
+        """``observer="prepared"``: the caller has already run ``ephemeris.stats`` on these very times
+        (which staged them on the device), set the observer scale and supplies ``outside_flags`` - used
+        when the samples of one job are split over several devices and the reductions are global."""
         if obstime is None:
             raise ValueError("obstime is required with an ephemeris")
         if ephemeris.device != self.device:
@@ -417,13 +420,19 @@ class DeviceModel:
         else:
             if out is None:
                 out = np.empty(shape, dtype=out_dtype)
-            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
-                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            elif out.shape != shape or out.dtype != out_dtype or out.strides[-1] != out.itemsize:
+                raise ValueError("out has wrong shape/dtype or its last axis is not contiguous")
             out_ptr = out.ctypes.data
+        out_row_stride = out.strides[0] // out.itemsize if (not device_mem and out.ndim == 2 and n > 1) else n
         if n == 0:
             return out
-        r_max = ephemeris.prepare(t_a, observer)
-        flags = spec_outside_flags(self.spec, r_max) if outside_flags is None else self._checked_flags(outside_flags)
+        if observer == "prepared":
+            if outside_flags is None:
+                raise ValueError("observer='prepared' needs outside_flags")
+            flags = self._checked_flags(outside_flags)
+        else:
+            r_max = ephemeris.prepare(t_a, observer)
+            flags = spec_outside_flags(self.spec, r_max) if outside_flags is None else self._checked_flags(outside_flags)
         args = _cabi.EvalArgs()
         args.n = n
         args.u, args.u_stride = u_ptr, u_stride
@@ -432,7 +441,7 @@ class DeviceModel:
         args.precision = _PRECISIONS[precision]
         args.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
         args.memory = _cabi.MEM_DEVICE if device_mem else _cabi.MEM_HOST
-        args.out, args.out_stride = out_ptr, n
+        args.out, args.out_stride = out_ptr, out_row_stride
         args.stream = stream
         # host arrays: prepare() -> zodi_ephemeris_stats staged the times on the device; obstime = NULL
         # integrates from that copy, so they cross the bus once
@@ -472,6 +481,7 @@ class DeviceModel:
         out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
         shape = (self.ncomps, n) if return_comps else (n,)
         on_device = device_out or peer_map is not None
+        out_row_stride = n
         keep = []
         if on_device:
             import torch
@@ -496,9 +506,12 @@ class DeviceModel:
             obs_ptr, earth_ptr, stream = obs_h.ctypes.data, earth_h.ctypes.data, None
             if out is None:
                 out = np.empty(shape, dtype=out_dtype)
-            elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
-                raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+            elif out.shape != shape or out.dtype != out_dtype or out.strides[-1] != out.itemsize:
+                # rows may be strided (a column block of a larger (ncomps, npix) map: one device's share)
+                raise ValueError("out has wrong shape/dtype or its last axis is not contiguous")
             out_ptr = out.ctypes.data
+            if out.ndim == 2 and n > 1:
+                out_row_stride = out.strides[0] // out.itemsize
         if n == 0:
             return out
         if peer_map is not None:
@@ -517,7 +530,7 @@ class DeviceModel:
         a.precision = _PRECISIONS[precision]
         a.out_dtype = _cabi.OUT_F64 if out_dtype == np.float64 else _cabi.OUT_F32
         a.memory = _cabi.MEM_DEVICE if on_device else _cabi.MEM_HOST
-        a.out, a.out_stride = out_ptr, n
+        a.out, a.out_stride = out_ptr, out_row_stride
         a.stream = stream
         if peer_map is not None:
             a.n_peers = len(peer_map.pointers)
@@ -657,6 +670,111 @@ class MultiDeviceModel:
                               out=out_part, out_dtype=out_part.dtype, outside_flags=flags)
 
         return self._run(lon.size, obs, earth, return_comps, out, out_dtype, outside_flags, call)
+
+
+    def evaluate_healpix(self, nside: int, obs, earth=None, *, pix_range=None, rot=None, nest: bool = False,
+                         return_comps: bool = False, precision: str = "fp64", out=None, out_dtype=None):
+        """Like :meth:`DeviceModel.evaluate_healpix` (host output), the pixel range split over ``devices``
+        by the ``np.array_split`` rule: every GPU generates its own directions, integrates them and writes
+        its share of the map straight into ``out`` over its own PCIe link (only the map crosses the bus)."""
+        nside = int(nside)
+        npix = 12 * nside * nside
+        lo, hi = (0, npix) if pix_range is None else (int(pix_range[0]), int(pix_range[1]))
+        if not 0 <= lo <= hi <= npix:
+            raise ValueError("pix_range outside the map")
+
+        def call(m, a, b, o, e, out_part, flags):
+            m.evaluate_healpix(nside, o, e, pix_range=(lo + a, lo + b), rot=rot, nest=nest, return_comps=return_comps,
+                               precision=precision, out=out_part, out_dtype=out_part.dtype)
+
+        obs = np.asarray(obs, dtype=np.float64).reshape(3, -1)
+        if obs.shape[1] != 1:
+            raise ValueError("evaluate_healpix takes a single observer position")
+        return self._run(hi - lo, obs, earth, return_comps, out, out_dtype, np.zeros((self.ncomps, 2), np.uint8), call)
+
+    def ephemeris(self, t0: float, dt: float, earth_knots, obs_knots=None) -> "MultiDeviceEphemeris":
+        """The same ephemeris splines on every device of this model (for :meth:`evaluate_tod`)."""
+        return MultiDeviceEphemeris(t0, dt, earth_knots, obs_knots, self.devices)
+
+    def evaluate_tod(self, u, obstime, ephemeris: "MultiDeviceEphemeris", *, observer: str = "earth", lonlat=None,
+                     rot=None, return_comps: bool = False, precision: str = "fp64", out=None, out_dtype=None):
+        """Time-ordered data with on-device ephemerides, the samples split over ``devices``.
+
+        ``u`` (3, N) unit vectors, or ``lonlat=(lon, lat)`` [rad] with the optional frame rotation ``rot``;
+        ``obstime`` (N,).  The reductions the reference's semantics need over ALL samples (sum |earth|^2 for
+        the semb-l2 norm, quirk Q5; largest observer distance for the early-out flags, quirk Q1) are formed
+        per device by ``zodi_ephemeris_stats`` - which also stages each shard's times on its device - and
+        combined on the host before any device integrates, so the result is bit-identical to one device.
+        """
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .sharding import split_bounds
+
+        if ephemeris.devices != self.devices:
+            raise ValueError("ephemeris was built for other devices")
+        t = np.ascontiguousarray(obstime, dtype=np.float64).reshape(-1)
+        n = t.size
+        if lonlat is None:
+            u = np.asarray(u, dtype=np.float64)
+            if u.ndim != 2 or u.shape != (3, n):
+                raise ValueError("unit_vectors must have shape (3, n) with one obstime per vector")
+        else:
+            lon = np.ascontiguousarray(lonlat[0], dtype=np.float64).reshape(-1)
+            lat = np.ascontiguousarray(lonlat[1], dtype=np.float64).reshape(-1)
+            if lon.size != n or lat.size != n:
+                raise ValueError("lon / lat / obstime must have the same length")
+        out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
+        shape = (self.ncomps, n) if return_comps else (n,)
+        if out is None:
+            out = np.empty(shape, dtype=out_dtype)
+        elif out.shape != shape or out.dtype != out_dtype or not out.flags.c_contiguous:
+            raise ValueError("out has wrong shape/dtype or is not C-contiguous")
+        if n == 0:
+            return out
+        parts = len(self.models) if n >= self.MIN_LOS_PER_DEVICE * len(self.models) else 1
+        shards = [(k, lo, hi) for k, (lo, hi) in enumerate(split_bounds(n, parts)) if hi > lo]
+        if observer == "knots" and not ephemeris.has_obs_knots:
+            raise ValueError("this ephemeris has no observer knots")
+        if observer in ("earth", "semb-l2") and ephemeris.has_obs_knots:
+            raise ValueError("this ephemeris carries observer knots; use observer='knots'")
+        if observer not in ("earth", "semb-l2", "knots"):
+            raise ValueError("observer must be 'earth', 'semb-l2' or 'knots'")
+        with ThreadPoolExecutor(max_workers=len(shards)) as pool:
+            for k, _, _ in shards:
+                ephemeris.parts[k].set_obs_scale(1.0)
+            stats = list(pool.map(lambda sh: ephemeris.parts[sh[0]].stats(t[sh[1]:sh[2]]), shards))
+            sum_r2 = float(np.sum([s[0] for s in stats]))
+            scale = 1.0
+            if observer == "semb-l2":
+                norm = float(np.sqrt(sum_r2))
+                scale = (norm + MEAN_DIST_TO_L2) / norm
+            r_max = max(s[2] for s in stats) if observer == "knots" else scale * max(s[1] for s in stats)
+            flags = spec_outside_flags(self.spec, r_max)
+
+            def work(sh):
+                k, lo, hi = sh
+                eph, m = ephemeris.parts[k], self.models[k]
+                eph.set_obs_scale(scale)
+                ll = None if lonlat is None else _LonLat(lon[lo:hi], lat[lo:hi], rot)
+                m.evaluate(None if ll is not None else u[:, lo:hi], ephemeris=eph, obstime=t[lo:hi], observer="prepared",
+                           lonlat=ll, return_comps=return_comps, precision=precision, out=out[..., lo:hi],
+                           out_dtype=out_dtype, outside_flags=flags)
+
+            list(pool.map(work, shards))
+        return out
+
+
+class MultiDeviceEphemeris:
+    """One :class:`DeviceEphemeris` per device of a :class:`MultiDeviceModel` (same knots everywhere)."""
+
+    def __init__(self, t0: float, dt: float, earth_knots, obs_knots=None, devices=(0,)):
+        self.devices = [int(d) for d in devices]
+        self.parts = [DeviceEphemeris(t0, dt, earth_knots, obs_knots, device=d) for d in self.devices]
+        self.has_obs_knots = obs_knots is not None
+
+    def close(self) -> None:
+        for p in self.parts:
+            p.close()
 
 
 class DeviceMultiBand(DeviceModel):

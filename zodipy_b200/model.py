@@ -13,8 +13,11 @@ positions interpolated with SciPy as in the reference | "device": hourly knots u
 interpolated in the kernel prologue), ``sky_rotation`` ("device": SkyCoord longitudes /
 latitudes are uploaded as they are and the rotation to the mean ecliptic happens in the kernel
 prologue whenever Astropy's transformation of the frame is a fixed rotation | "host": every
-coordinate is transformed by Astropy as in the reference).  ``nprocesses`` is accepted for API
-compatibility and ignored: the GPU path has no use for host worker processes.
+coordinate is transformed by Astropy as in the reference), ``devices`` (several CUDA ordinals driven
+by this one process for host arrays).  ``nprocesses=k`` of ``evaluate`` - the reference's number of
+fork-pool workers (``zodipy/model.py:182-198``) - maps to ``min(k, visible GPUs)`` devices when neither
+``device`` nor ``devices`` was given and the process is not one rank of a one-process-per-GPU job
+(``LOCAL_RANK`` unset); the split rule (``np.array_split``) and the results are the reference's.
 """
 from __future__ import annotations
 
@@ -81,6 +84,8 @@ class Model:
             if not devices or (device is not None and int(device) != devices[0]):
                 raise ValueError("devices must be a non-empty list whose first entry equals device (if given)")
             device = devices[0]
+        # nprocesses -> devices only when the caller left the placement to us (see module docstring)
+        self._auto_devices = device is None and devices is None and "LOCAL_RANK" not in os.environ
         self._device = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
         self._devices = devices if devices is not None else [self._device]
         self._device_model: DeviceModel | None = None
@@ -123,6 +128,31 @@ class Model:
             self._multi_model = MultiDeviceModel(self._spec, self._devices)
         return self._multi_model
 
+    def _use_processes(self, nprocesses: int) -> None:
+        """``nprocesses=k`` -> ``min(k, visible GPUs)`` devices (``zodipy/model.py:182-198`` splits the
+        coordinates over k workers; here the workers are GPUs driven by threads of this process)."""
+        if not self._auto_devices or nprocesses is None or int(nprocesses) <= 1:
+            return
+        from . import _cabi
+
+        k = max(1, min(int(nprocesses), _cabi.device_count()))
+        wanted = list(range(k))
+        if wanted != self._devices:
+            if self._multi_model is not None:
+                self._multi_model.close()
+                self._multi_model = None
+            self._devices = wanted
+            self._device = wanted[0]
+
+    def ephemeris(self, t0: float, dt: float, earth_knots, obs_knots=None):
+        """Device-resident ephemeris splines for :meth:`evaluate_tod_xyz` / :meth:`evaluate_lonlat`, on
+        every device this model drives (hourly knots ``t0 + k dt`` as in ``zodipy/bodies.py:16-35``)."""
+        from .engine import DeviceEphemeris, MultiDeviceEphemeris
+
+        if len(self._devices) > 1:
+            return MultiDeviceEphemeris(t0, dt, earth_knots, obs_knots, self._devices)
+        return DeviceEphemeris(t0, dt, earth_knots, obs_knots, device=self._device)
+
     # ---------------------------------------------------------------------------------------
     def evaluate_xyz(self, unit_vectors, obs_xyz, earth_xyz=None, *, return_comps: bool = False,
                      precision: str | None = None, out=None, out_dtype=None, outside_flags=None):
@@ -154,6 +184,10 @@ class Model:
         "knots".  Equivalent to ``evaluate_xyz(u, obs_xyz(t), earth_xyz(t))`` with the positions
         from ``scipy.interpolate.CubicSpline`` - without computing or uploading them on the host.
         """
+        if hasattr(ephemeris, "parts"):  # MultiDeviceEphemeris: samples split over the devices
+            return self._multi(unit_vectors).evaluate_tod(
+                unit_vectors, obstime, ephemeris, observer=observer, return_comps=return_comps,
+                precision=precision or self._precision, out=out, out_dtype=out_dtype)
         return self.device_model.evaluate(
             unit_vectors, return_comps=return_comps, precision=precision or self._precision, out=out,
             out_dtype=out_dtype, ephemeris=ephemeris, obstime=obstime, observer=observer)
@@ -167,6 +201,10 @@ class Model:
         unit vectors of ``zodipy/model.py:247-251`` are formed and rotated in the kernel prologue,
         so the host neither builds nor uploads the (3, N) array (16 instead of 24 B per line of
         sight cross the bus)."""
+        if ephemeris is not None and hasattr(ephemeris, "parts"):
+            return self._multi(lon, lat).evaluate_tod(
+                None, obstime, ephemeris, observer=observer, lonlat=(lon, lat), rot=frame_rotation,
+                return_comps=return_comps, precision=precision or self._precision, out=out, out_dtype=out_dtype)
         multi = self._multi(lon, lat) if ephemeris is None else None
         if multi is not None:
             return multi.evaluate_lonlat(lon, lat, obs_xyz, earth_xyz, rot=frame_rotation, return_comps=return_comps,
@@ -188,6 +226,11 @@ class Model:
         without building or uploading the (3, N) direction array.  ``frame_rotation`` is the 3x3
         matrix taking pixel-frame vectors to mean-ecliptic ones (identity if the map is ecliptic).
         """
+        multi = None if device_out else self._multi()
+        if multi is not None:
+            return multi.evaluate_healpix(nside, obs_xyz, earth_xyz, pix_range=pix_range, rot=frame_rotation, nest=nest,
+                                          return_comps=return_comps, precision=precision or self._precision, out=out,
+                                          out_dtype=out_dtype)
         return self.device_model.evaluate_healpix(
             nside, obs_xyz, earth_xyz, pix_range=pix_range, rot=frame_rotation, nest=nest,
             return_comps=return_comps, precision=precision or self._precision, out=out,
@@ -214,6 +257,7 @@ class Model:
         if skycoord.obstime.size > skycoord.size:
             raise ValueError("The size of obstime must be either 1 or ncoords.")
 
+        self._use_processes(nprocesses)
         from . import astro  # lazy: needs astropy
 
         # directions: angles + one 3x3 matrix for the device, or Astropy-transformed vectors
@@ -224,7 +268,7 @@ class Model:
             if obspos_isstr and self._tod_ephemeris == "device" and interp_obstimes.size >= 4:
                 # hourly knots -> device splines; per-sample interpolation in the kernel prologue
                 eph, mode, u_xyz, mjd = astro.device_ephemeris(
-                    skycoord, obspos, interp_obstimes, self._ephemeris, self._device, with_directions=sky is None)
+                    skycoord, obspos, interp_obstimes, self._ephemeris, self._devices, with_directions=sky is None)
                 if sky is None:
                     emission = self.evaluate_tod_xyz(u_xyz, mjd, eph, observer=mode, return_comps=return_comps)
                 else:
