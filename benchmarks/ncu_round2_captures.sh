@@ -9,6 +9,8 @@ TAG="${NCU_TAG:-r2}"
 for w in $WHAT; do
   case $w in
     x2) name=${TAG}_x2_planck18_nside2048; args="--name planck18 --x 857 --unit GHz --nside 2048";;
+    x2a) name=${TAG}_x2_planck18_nside2048_arrays; args="--name planck18 --x 857 --unit GHz --nside 2048 --arrays";;
+    fp64a) name=${TAG}_fp64_planck18_nside2048_arrays; args="--name planck18 --x 857 --unit GHz --nside 2048 --precision fp64 --arrays";;
     dirbe) name=${TAG}_x2_dirbe_nside1024; args="--name dirbe --x 25 --unit um --nside 1024";;
     dirbe64) name=${TAG}_x2_dirbe_nside64; args="--name dirbe --x 25 --unit um --nside 64";;
     fp64) name=${TAG}_fp64_planck18_nside1024; args="--name planck18 --x 857 --unit GHz --nside 1024 --precision fp64";;

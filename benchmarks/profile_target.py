@@ -27,11 +27,29 @@ def main() -> None:
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--nside", type=int, default=1024)
     ap.add_argument("--launches", type=int, default=3)
+    ap.add_argument("--arrays", action="store_true",
+                    help="device-resident (3, N) unit vectors as input (bench.py's `value` path) instead of "
+                         "directions generated in the kernel prologue")
     args = ap.parse_args()
     model = zp.Model(zp.Quantity(args.x, args.unit), name=args.name, precision=args.precision)
     dtype = np.float32 if args.precision == "fp32" else np.float64
+    if args.arrays:
+        from zodipy_b200 import engine
+
+        n = 12 * args.nside**2
+        dev = torch.device("cuda", 0)
+        u = torch.empty((3, n), dtype=torch.float64, device=dev)
+        cabi = engine._cabi
+        cabi.check(cabi.load().zodi_healpix_vectors(0, args.nside, 0, 0, n, None, u.data_ptr(), n, cabi.MEM_DEVICE, None))
+        obs = torch.as_tensor(EARTH, device=dev)
+        flags = model.device_model.outside_flags(EARTH)
+        out = torch.empty(n, dtype=torch.float32 if args.precision == "fp32" else torch.float64, device=dev)
     for _ in range(args.launches):
-        model.evaluate_healpix(args.nside, EARTH, device_out=True, out_dtype=dtype)
+        if args.arrays:
+            model.device_model.evaluate(u, obs, obs, precision=args.precision, out=out, out_dtype=dtype,
+                                        outside_flags=flags)
+        else:
+            model.evaluate_healpix(args.nside, EARTH, device_out=True, out_dtype=dtype)
     torch.cuda.synchronize()
     print(model.device_model.kernel_name_for(12 * args.nside**2, args.precision))
 
