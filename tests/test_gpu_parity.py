@@ -714,13 +714,17 @@ def test_multi_device_tod_and_healpix_bitwise(observer, monkeypatch):
     assert hasattr(ephn, "parts") and len(ephn.parts) == 3
     ref = one.evaluate_tod_xyz(u, t, eph1, observer=observer, return_comps=True)
     got = many.evaluate_tod_xyz(u, t, ephn, observer=observer, return_comps=True)
-    if observer == "earth":
-        np.testing.assert_array_equal(got, ref)
-    else:  # the global sum |earth|^2 is added in another order: scale equal to ~1 ulp
-        np.testing.assert_allclose(got, ref, rtol=2e-6)
+    # shards of this size take another lane split than the whole (summation order of the lane partials), and
+    # the global sum |earth|^2 of semb-l2 is added in another order (scale equal to ~1 ulp)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
+    if observer == "earth":  # same launch shape everywhere -> bit-identical
+        monkeypatch.setenv("ZODI_X2_LANES", "2")
+        np.testing.assert_array_equal(many.evaluate_tod_xyz(u, t, ephn, observer=observer, return_comps=True),
+                                      one.evaluate_tod_xyz(u, t, eph1, observer=observer, return_comps=True))
     lon, lat = np.arctan2(u[1], u[0]), np.arcsin(np.clip(u[2], -1, 1))
     np.testing.assert_allclose(many.evaluate_lonlat(lon, lat, ephemeris=ephn, obstime=t, observer=observer),
                                one.evaluate_lonlat(lon, lat, ephemeris=eph1, obstime=t, observer=observer), rtol=2e-6)
+    monkeypatch.setenv("ZODI_X2_LANES", "2")
     for kwargs in ({}, {"return_comps": True}, {"pix_range": (1000, 150_001), "nest": True}):
         np.testing.assert_array_equal(many.evaluate_healpix(128, EARTH_20220114, out_dtype=np.float32, **kwargs),
                                       one.evaluate_healpix(128, EARTH_20220114, out_dtype=np.float32, **kwargs))

@@ -160,6 +160,38 @@ def test_sky_rotation_is_read_off_the_frame_transformation(ap, oracle_seam):
         zp.Model(25 * units.micron, sky_rotation="gpu")
 
 
+def test_sky_rotation_with_per_sample_frame_attributes(ap, oracle_seam):
+    """Time-ordered SkyCoords whose FRAME carries the N-element obstime (Astropy frames such as
+    HeliocentricMeanEcliptic do): the probe directions are attached to a copy of the frame with scalar
+    attributes, so the device-rotation path is taken; a frame whose orientation really depends on the
+    per-sample attribute is detected and falls back to the host transformation with a warning."""
+    import zodipy_b200 as zp
+    from zodipy_b200 import astro
+
+    units, time, coords = ap
+    if not hasattr(coords, "ObstimeEcliptic"):
+        pytest.skip("stand-in frames (real Astropy is covered by tools/verify_with_astropy.py)")
+    n = 40
+    times = time.Time(59215.0 + np.linspace(0.0, 30.0, n), format="mjd")
+    rng = np.random.default_rng(8)
+    lon, lat = rng.uniform(0, 360, n), rng.uniform(-90, 90, n)
+    sc = coords.SkyCoord(lon, lat, unit=units.deg, frame=coords.ObstimeEcliptic(obstime=times))
+    assert sc.frame.obstime.size == n and sc.obstime.size == n
+    got = astro.sky_lonlat_rotation(sc)
+    assert got is not None, "per-sample frame attributes must not disable the device rotation"
+    np.testing.assert_allclose(got[2], np.eye(3), rtol=0, atol=1e-15)
+    dev = zp.Model(25 * units.micron, sky_rotation="device").evaluate(sc)
+    host = zp.Model(25 * units.micron, sky_rotation="host").evaluate(sc)
+    np.testing.assert_allclose(np.asarray(dev), np.asarray(host), rtol=1e-12)
+    turning = coords.SkyCoord(lon, lat, unit=units.deg, frame=coords.TimeDependentFrame(obstime=times))
+    with pytest.warns(RuntimeWarning, match="not a fixed rotation"):
+        assert astro.sky_lonlat_rotation(turning) is None
+    with pytest.warns(RuntimeWarning):
+        fallback = zp.Model(25 * units.micron, sky_rotation="device").evaluate(turning)
+    np.testing.assert_allclose(np.asarray(fallback),
+                               np.asarray(zp.Model(25 * units.micron, sky_rotation="host").evaluate(turning)), rtol=1e-12)
+
+
 def test_time_ordered_inputs(ap, oracle_seam):
     import zodipy_b200 as zp
 

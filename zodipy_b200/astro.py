@@ -52,35 +52,85 @@ _PROBE_LON = np.array([0.0, 0.5 * np.pi, 0.0, 0.7, 4.1])
 _PROBE_LAT = np.array([0.0, 0.0, 0.5 * np.pi, -0.4, 1.1])
 
 
+def _scalar_frame(frame, pick):
+    """Data-less copy of ``frame`` in which every array-valued frame attribute (e.g. a per-sample
+    ``obstime``) is replaced by its element ``pick`` (0 or -1), so that a few probe directions can be
+    attached to it.  Returns (frame, any attribute was an array)."""
+    names = getattr(frame, "frame_attributes", None)
+    if names is None:  # old Astropy spelling
+        names = frame.get_frame_attr_names()
+    attrs, varying = {}, False
+    for name in names:
+        value = getattr(frame, name)
+        if getattr(value, "shape", ()) not in ((), None) and getattr(value, "size", 1) > 1:
+            value, varying = value[pick], True
+        attrs[name] = value
+    return type(frame)(**attrs), varying
+
+
+def _probe_rotation(frame):
+    """(R, ok): the 3x3 matrix Astropy's transformation frame -> BarycentricMeanEcliptic applies to the
+    frame's axes, and whether two further directions confirm that the transformation IS that rotation."""
+    probe = coords.SkyCoord(_PROBE_LON * units.rad, _PROBE_LAT * units.rad, frame=frame)
+    xyz = np.asarray(probe.transform_to(coords.BarycentricMeanEcliptic).cartesian.xyz.value, dtype=np.float64)
+    rot = np.ascontiguousarray(xyz[:, :3])  # columns = images of the frame's x, y, z axes
+    cl = np.cos(_PROBE_LAT[3:])
+    src = np.array([cl * np.cos(_PROBE_LON[3:]), cl * np.sin(_PROBE_LON[3:]), np.sin(_PROBE_LAT[3:])])
+    ok = (np.allclose(rot.T @ rot, np.eye(3), rtol=0, atol=1e-12)
+          and np.allclose(rot @ src, xyz[:, 3:], rtol=0, atol=1e-12))
+    return rot, bool(ok)
+
+
 def sky_lonlat_rotation(skycoord):
     """``(lon, lat, R)`` with the mean-ecliptic unit vectors equal to
     ``R @ (cos lat cos lon, cos lat sin lon, sin lat)``, or ``None``.
 
     ``skycoord.transform_to(BarycentricMeanEcliptic).cartesian.xyz`` (``model.py:247-251``) is, for
     direction-only coordinates in ICRS / Galactic / FK5 / mean-ecliptic frames, a fixed rotation of
-    the sphere.  R is read off Astropy itself by transforming the three axes of the input frame,
-    and two more probe directions verify that the transformation really is that rotation (frames
-    with aberration, per-sample frame attributes or distances fail the check or raise, and the
-    caller falls back to transforming every coordinate on the host).  The angles then go to the
-    device as they are (16 B per line of sight) and the kernel prologue does the trigonometry.
+    the sphere.  R is read off Astropy itself: probe directions are attached to a data-less copy of the
+    coordinate's frame (array-valued frame attributes such as the per-sample ``obstime`` of time-ordered
+    data reduced to their first - and, for comparison, last - element), the images of the three axes
+    give R, two more directions verify that the transformation really is that rotation, and finally a
+    handful of the ACTUAL coordinates are transformed by Astropy and compared with ``R @ vector``.
+    Frames that fail any of these (aberration, time-dependent orientation, distances) make the caller
+    fall back to transforming every coordinate on the host, with a warning saying why.  The angles then
+    go to the device as they are (16 B per line of sight) and the kernel prologue does the trigonometry.
     """
+    import warnings
+
+    def give_up(why):
+        warnings.warn(f"sky_rotation='device' is not applicable ({why}); coordinates are transformed on the "
+                      "host as in the reference", RuntimeWarning, stacklevel=3)
+        return None
+
+    data = skycoord.data
+    if not isinstance(data, coords.UnitSphericalRepresentation):
+        return None  # distances / cartesian data: not a pure direction, the reference path handles it
+    lon = np.ascontiguousarray(np.atleast_1d(data.lon.to_value(units.rad)), dtype=np.float64).reshape(-1)
+    lat = np.ascontiguousarray(np.atleast_1d(data.lat.to_value(units.rad)), dtype=np.float64).reshape(-1)
     try:
-        data = skycoord.data
-        if not isinstance(data, coords.UnitSphericalRepresentation):
-            return None
-        lon = np.ascontiguousarray(np.atleast_1d(data.lon.to_value(units.rad)), dtype=np.float64).reshape(-1)
-        lat = np.ascontiguousarray(np.atleast_1d(data.lat.to_value(units.rad)), dtype=np.float64).reshape(-1)
-        frame = skycoord.frame.replicate_without_data()
-        probe = coords.SkyCoord(_PROBE_LON * units.rad, _PROBE_LAT * units.rad, frame=frame)
-        xyz = np.asarray(probe.transform_to(coords.BarycentricMeanEcliptic).cartesian.xyz.value, dtype=np.float64)
-    except Exception:  # anything unusual about the frame: keep the reference's host transformation
-        return None
-    rot = np.ascontiguousarray(xyz[:, :3])  # columns = images of the frame's x, y, z axes
-    cl = np.cos(_PROBE_LAT[3:])
-    src = np.array([cl * np.cos(_PROBE_LON[3:]), cl * np.sin(_PROBE_LON[3:]), np.sin(_PROBE_LAT[3:])])
-    if not (np.allclose(rot.T @ rot, np.eye(3), rtol=0, atol=1e-12)
-            and np.allclose(rot @ src, xyz[:, 3:], rtol=0, atol=1e-12)):
-        return None
+        frame0, varying = _scalar_frame(skycoord.frame, 0)
+        rot, ok = _probe_rotation(frame0)
+        if ok and varying:  # per-sample frame attributes: the rotation must not depend on them
+            rot_last, ok_last = _probe_rotation(_scalar_frame(skycoord.frame, -1)[0])
+            ok = ok_last and np.allclose(rot, rot_last, rtol=0, atol=1e-12)
+    except (TypeError, ValueError, AttributeError, KeyError, IndexError, coords.ConvertError) as error:
+        return give_up(f"{type(error).__name__}: {error}")
+    if not ok:
+        return give_up("the frame's transformation to BarycentricMeanEcliptic is not a fixed rotation")
+    # last line of defence: Astropy's own transformation of a few of the actual coordinates
+    n = lon.size
+    if n > 0 and not getattr(skycoord, "isscalar", False):
+        idx = np.unique(np.linspace(0, n - 1, min(n, 8)).astype(np.int64))
+        try:
+            want = np.asarray(skycoord[idx].transform_to(coords.BarycentricMeanEcliptic).cartesian.xyz.value,
+                              dtype=np.float64).reshape(3, -1)
+        except (TypeError, ValueError, AttributeError, KeyError, IndexError, coords.ConvertError) as error:
+            return give_up(f"{type(error).__name__}: {error}")
+        cl = np.cos(lat[idx])
+        have = rot @ np.array([cl * np.cos(lon[idx]), cl * np.sin(lon[idx]), np.sin(lat[idx])])
+        if not np.allclose(have, want, rtol=0, atol=1e-11):
+            return give_up("Astropy's transformation of the coordinates differs from the probed rotation")
     return lon, lat, rot
 
 

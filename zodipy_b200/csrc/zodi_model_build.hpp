@@ -103,6 +103,7 @@ inline void derive_component(const zodi_model_desc& d, const zodi_component_desc
             o.s[0] = p[0]; o.s[1] = 1.0 / p[1]; o.s[2] = -0.5 * p[2];
             o.s[3] = p[3] * std::pow(p[5], p[2]); o.s[4] = p[4] * p[4]; o.s[5] = p[5] * p[5];
             o.s[6] = -0.5 * kLog2e;
+            o.s[7] = (p[2] == 1.0) ? 1.0 : 0.0;  // gamma == 1: R^-gamma is 1 / R (fused RRM kernel)
             break;
     }
 }

@@ -56,6 +56,15 @@ ZODI_HD RrmNode<Real> rrm_node(const RrmModel<Real>& R, int slot, const Pair<Rea
     return s;
 }
 
+// Node k of a rule split over L lanes with a warp-uniform trip count: surplus iterations re-evaluate the
+// last node with weight 0 (loops whose bodies contain warp votes).
+template <typename Real>
+ZODI_HD Pair<Real> rrm_lane_node(const Pair<Real>* nodes, int n_nodes, int k) {
+    Pair<Real> nw = nodes[k < n_nodes ? k : n_nodes - 1];
+    if (k >= n_nodes) nw.b = Real(0);
+    return nw;
+}
+
 // Latitude of the node above the component's symmetry plane: asin(Z_c / R_c), clipped like the
 // reference's arcsin argument can only be by rounding.
 template <typename Real>
@@ -69,13 +78,22 @@ ZODI_HD Real rrm_latitude(const DevComp<Real>& c, const RrmNode<Real>& s, Real r
 template <typename Real, bool WITH_Q>
 ZODI_HD Real rrm_fan_like(const DevComp<Real>& c, const RrmNode<Real>& s) {
     using M = Math<Real>;
-    if (!(s.R2 >= c.s[4] && s.R2 <= c.s[5])) return Real(0);
+    // outside [R_inner, R_outer] the density is 0 (boolean-mask gather / scatter of the reference); the value
+    // is selected at the end so that every lane reaches the warp vote below
+    const bool in_range = s.R2 >= c.s[4] && s.R2 <= c.s[5];
     Real Zc;
     const Real beta = rrm_latitude<Real>(c, s, M::rsqrt_(s.R2), Zc);
     const Real za = M::abs_(Zc);
-    const Real ep = (za < c.s[6]) ? Real(2) - za * c.s[1] : Real(1);
     const Real ab = M::abs_(beta);
-    const Real bp = (ab > Real(0)) ? M::exp2_(ep * M::log2_(ab)) : Real(0);
+    // |beta|^epsilon with epsilon = 2 - |Z_c| / Z_0 inside the slab |Z_c| < Z_0 and 1 outside it, where the
+    // power is the identity (np.power(x, 1.0) == x): the log2 / exp2 pair runs only for warps with a lane
+    // inside the slab (a few per cent of the nodes)
+    Real bp = ab;
+    const bool in_slab = za < c.s[6];
+    if (warp_any(in_slab)) {
+        const Real pw = (ab > Real(0)) ? M::exp2_((Real(2) - za * c.s[1]) * M::log2_(ab)) : Real(0);
+        bp = in_slab ? pw : ab;
+    }
     Real lg = c.s[2] * M::sin_(bp);
     if (WITH_Q) {
         // cos(beta)^Q = (rho / R)^Q with rho the in-plane distance (no cancellation near the poles)
@@ -83,25 +101,30 @@ ZODI_HD Real rrm_fan_like(const DevComp<Real>& c, const RrmNode<Real>& s) {
         const Real rho2 = M::fma_(px, px, M::fma_(py, py, pz * pz));
         lg = M::fma_(Real(0.5) * c.s[7], M::log2_(rho2) - s.lgR2, lg);
     }
-    return c.s[3] * M::exp2_(M::fma_(c.s[0], s.lgR2, lg));
+    return in_range ? c.s[3] * M::exp2_(M::fma_(c.s[0], s.lgR2, lg)) : Real(0);
 }
 
 // Narrow band given the latitude in degrees (absolute value), number_density.py:267-304.
 template <typename Real>
 ZODI_HD Real rrm_narrow(const DevComp<Real>& c, const RrmNode<Real>& s, Real abs_lat_deg) {
     using M = Math<Real>;
-    if (!(s.R2 >= c.s[4] && s.R2 <= c.s[5]) || !(abs_lat_deg < c.s[0])) return Real(0);
-    return c.s[3] * M::exp2_(M::fma_(c.s[2], s.lgR2, c.s[1] * (abs_lat_deg - c.s[0])));
+    const bool inside = (s.R2 >= c.s[4] && s.R2 <= c.s[5]) && (abs_lat_deg < c.s[0]);
+    Real n = Real(0);
+    // the band is a few degrees wide: most warps have no lane inside it and skip the exponential
+    if (warp_any(inside)) n = inside ? c.s[3] * M::exp2_(M::fma_(c.s[2], s.lgR2, c.s[1] * (abs_lat_deg - c.s[0]))) : Real(0);
+    return n;
 }
 
 // Broad band given the signed latitude in degrees, number_density.py:307-342.
 template <typename Real>
-ZODI_HD Real rrm_broad(const DevComp<Real>& c, const RrmNode<Real>& s, Real lat_deg) {
+ZODI_HD Real rrm_broad(const DevComp<Real>& c, const RrmNode<Real>& s, Real lat_deg, Real rinv) {
     using M = Math<Real>;
-    if (!(s.R2 >= c.s[4] && s.R2 <= c.s[5])) return Real(0);
+    if (!(s.R2 >= c.s[4] && s.R2 <= c.s[5])) return Real(0);  // no vote below: lanes may leave early
     const Real a = (lat_deg - c.s[0]) * c.s[1], b = (lat_deg + c.s[0]) * c.s[1];
     const Real f = M::exp2_(c.s[6] * a * a) + M::exp2_(c.s[6] * b * b);
-    return c.s[3] * f * M::exp2_(c.s[2] * s.lgR2);
+    // (R / R_outer)^-gamma: gamma == 1 in the shipped model, where it is 1 / R itself
+    const Real rp = (c.s[7] != Real(0)) ? rinv : M::exp2_(c.s[2] * s.lgR2);
+    return c.s[3] * f * rp;
 }
 
 template <typename Real, typename Emit>
@@ -120,16 +143,16 @@ ZODI_HD void integrate_rrm(const RrmModel<Real>& R, const Pair<Real>* tab, const
     // ---- fan, comet: own grids ----
     interval(R_FAN, h, mid);
     Real acc = Real(0);
-    for (int k = sub; k < R.n_nodes; k += L) {
-        const RrmNode<Real> s = rrm_node<Real>(R, R_FAN, tab, nodes[k], h, mid, G);
+    for (int k0 = 0; k0 < R.n_nodes; k0 += L) {  // warp-uniform trip count: the densities contain warp votes
+        const RrmNode<Real> s = rrm_node<Real>(R, R_FAN, tab, rrm_lane_node<Real>(nodes, R.n_nodes, k0 + sub), h, mid, G);
         acc = M::fma_(s.wB, rrm_fan_like<Real, true>(R.c[R_FAN], s), acc);
     }
     emit(R_FAN, acc * (R.e1 * h));
 
     interval(R_COMET, h, mid);
     acc = Real(0);
-    for (int k = sub; k < R.n_nodes; k += L) {
-        const RrmNode<Real> s = rrm_node<Real>(R, R_COMET, tab, nodes[k], h, mid, G);
+    for (int k0 = 0; k0 < R.n_nodes; k0 += L) {
+        const RrmNode<Real> s = rrm_node<Real>(R, R_COMET, tab, rrm_lane_node<Real>(nodes, R.n_nodes, k0 + sub), h, mid, G);
         acc = M::fma_(s.wB, rrm_fan_like<Real, false>(R.c[R_COMET], s), acc);
     }
     emit(R_COMET, acc * (R.e1 * h));
@@ -137,8 +160,8 @@ ZODI_HD void integrate_rrm(const RrmModel<Real>& R, const Pair<Real>* tab, const
     // ---- the three asteroidal bands: one grid, shared source terms and 1/R ----
     interval(R_NB_IN, h, mid);
     Real a_in = Real(0), a_out = Real(0), a_bb = Real(0);
-    for (int k = sub; k < R.n_nodes; k += L) {
-        const RrmNode<Real> s = rrm_node<Real>(R, R_NB_IN, tab, nodes[k], h, mid, G);
+    for (int k0 = 0; k0 < R.n_nodes; k0 += L) {
+        const RrmNode<Real> s = rrm_node<Real>(R, R_NB_IN, tab, rrm_lane_node<Real>(nodes, R.n_nodes, k0 + sub), h, mid, G);
         const Real rinv = M::rsqrt_(s.R2);
         Real Zc;
         const Real lat_in = M::abs_(rrm_latitude<Real>(R.c[R_NB_IN], s, rinv, Zc)) * deg;
@@ -146,7 +169,7 @@ ZODI_HD void integrate_rrm(const RrmModel<Real>& R, const Pair<Real>* tab, const
         const Real lat_bb = rrm_latitude<Real>(R.c[R_BROAD], s, rinv, Zc) * deg;
         a_in = M::fma_(s.wB, rrm_narrow<Real>(R.c[R_NB_IN], s, lat_in), a_in);
         a_out = M::fma_(s.wB, rrm_narrow<Real>(R.c[R_NB_OUT], s, lat_out), a_out);
-        a_bb = M::fma_(s.wB, rrm_broad<Real>(R.c[R_BROAD], s, lat_bb), a_bb);
+        a_bb = M::fma_(s.wB, rrm_broad<Real>(R.c[R_BROAD], s, lat_bb, rinv), a_bb);
     }
     emit(R_NB_IN, a_in * (R.e1 * h));
     emit(R_NB_OUT, a_out * (R.e1 * h));

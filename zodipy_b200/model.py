@@ -135,7 +135,11 @@ class Model:
             return
         from . import _cabi
 
-        k = max(1, min(int(nprocesses), _cabi.device_count()))
+        try:
+            visible = _cabi.device_count()
+        except (_cabi.ZodiError, RuntimeError):
+            return  # no usable device: the evaluation itself reports that (there is no CPU fallback)
+        k = max(1, min(int(nprocesses), visible))
         wanted = list(range(k))
         if wanted != self._devices:
             if self._multi_model is not None:
