@@ -11,6 +11,7 @@
 
 #include "../../zodipy_b200/csrc/zodi_model_build.hpp"
 #include "../../zodipy_b200/csrc/zodi_kelsall_x2.cuh"
+#include "../../zodipy_b200/csrc/zodi_rrm_x2.cuh"
 
 using namespace zodi;
 
@@ -134,6 +135,31 @@ static void run_rrm(const RrmModel<Real>& R, const std::vector<Pair<Real>>& tab,
     }
 }
 
+// Packed fused RRM routines (zodi_rrm_x2.cuh), two lines of sight per "thread".
+static void run_rrm_x2(const RrmModelX2& X, const std::vector<Pair<float>>& tab, const std::vector<Pair<float>>& nodes,
+                       int64_t n, const double* u, const double* obs, int64_t n_obs, const double* earth,
+                       int64_t n_earth, const uint8_t* flags, double* out) {
+    uint32_t mask = 0;
+    for (int c = 0; c < R_NCOMPS; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+    for (int64_t j0 = 0; j0 < n; j0 += 2) {
+        const int64_t jj[2] = {j0, j0 + 1 < n ? j0 + 1 : j0};
+        LosPre P[2];
+        RrmIntervals I[2];
+        for (int q = 0; q < 2; ++q) {
+            const int64_t j = jj[q], jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+            rrm_pre(X, u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo], earth[je],
+                    earth[n_earth + je], mask, P[q], I[q]);
+        }
+        integrate_rrm_x2(X, tab.data(), nodes.data(), P[0], P[1], I[0], I[1], [&](int ci, float a, float b) {
+            out[ci * n + jj[1]] = b;
+            out[ci * n + jj[0]] = a;
+        });
+    }
+}
+
 // fast: 0 generic routine, 1 scalar fused routine, 2 packed fused routines (fp32, no scattering).
 // Returns 1 / 2 if the Kelsall fast path was eligible and used, 3 for the fused RRM routine, 0 if the
 // generic routine ran.
@@ -176,6 +202,11 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
             if (precision == ZODI_FP32) {
                 RrmModel<float> r32;
                 narrow_rrm(r64, m32, r32);
+                RrmModelX2 x2;
+                if (fast == 2 && build_rrm_x2(r64, r32, x2)) {
+                    run_rrm_x2(x2, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, out);
+                    return 4;
+                }
                 run_rrm<float>(r32, t32, n32, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
             } else {
                 run_rrm<double>(r64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);

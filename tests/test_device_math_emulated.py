@@ -22,7 +22,7 @@ SRC = os.path.join(HERE, "host_emu", "zodi_emu.cpp")
 LIB = os.path.join(HERE, "host_emu", "libzodi_emu.so")
 DEPS = [SRC] + [os.path.join(HERE, "..", "zodipy_b200", "csrc", f)
                 for f in ("zodi_device.cuh", "zodi_model_build.hpp", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh",
-                          "zodi_rrm.cuh")]
+                          "zodi_rrm.cuh", "zodi_rrm_x2.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -101,6 +101,19 @@ def test_fused_rrm_routine_matches_reference(emu, case_id, precision, lanes):
     tol, floor = (TOL_FP64, COMP_FLOOR_FP64) if precision == 0 else (TOL_FP32, 1.0)
     assert max_rel_total(em, a["emission"]) <= tol
     assert max_rel_comps(em, a["emission"], floor=floor) <= tol
+
+
+@pytest.mark.parametrize("case_id", [c for c in case_ids() if "rrm" in c])
+def test_packed_rrm_routines_match_scalar_and_reference(emu, case_id):
+    """Packed RRM routines (zodi_rrm_x2.cuh) against the scalar fused routine (same operations per line of
+    sight) and the reference's outputs."""
+    case, a = golden_case(case_id)
+    packed, used = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=2)
+    assert used == 4
+    scalar, _ = run_emu(emu, case["spec"], a["u"], a["obs"], a["earth"], 1, 1, fast=1)
+    np.testing.assert_allclose(packed, scalar, rtol=2e-6, atol=1e-30)
+    assert max_rel_total(packed, a["emission"]) <= TOL_FP32
+    assert max_rel_comps(packed, a["emission"], floor=1.0) <= TOL_FP32
 
 
 @pytest.mark.parametrize("case_id", case_ids())

@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libzodi_b200.so")
 HEADERS = ["zodi_device.cuh", "zodi_fp64_tables.cuh", "zodi_kernels.cuh", "zodi_kelsall.cuh", "zodi_kelsall_x2.cuh",
-           "zodi_multiband.cuh", "zodi_rrm.cuh", "zodi_misc_kernels.cuh", "zodi_model_build.hpp", "zodi_launch.hpp",
+           "zodi_multiband.cuh", "zodi_rrm.cuh", "zodi_rrm_x2.cuh", "zodi_misc_kernels.cuh", "zodi_model_build.hpp", "zodi_launch.hpp",
            os.path.join("..", "..", "include", "zodi_b200.h")]
 
 _TYPES = (("f32", "float"), ("f64", "double"))
@@ -28,7 +28,7 @@ UNITS = [("capi", "zodi_capi.cu", [])]
 for _suffix, _real in _TYPES:
     for _fam in ("generic", "kelsall", "multiband", "rrm"):
         UNITS.append((f"{_fam}_{_suffix}", f"zodi_launch_{_fam}.cu",
-                      [f"-DZODI_TU_REAL={_real}", f"-DZODI_TU_SUFFIX={_suffix}"]))
+                      [f"-DZODI_TU_REAL={_real}", f"-DZODI_TU_SUFFIX={_suffix}", f"-DZODI_TU_IS_{_suffix.upper()}"]))
 for _lanes in (1, 2, 4, 8):
     UNITS.append((f"x2_l{_lanes}", "zodi_launch_x2.cu", [f"-DZODI_TU_LANES={_lanes}"]))
 

@@ -153,6 +153,8 @@ struct zodi_model_s {
     bool rrm_ok = false;      // model fits the fused RRM kernel
     RrmModel<double> r64;
     RrmModel<float> r32;
+    bool rrm_x2_ok = false;   // ... and its packed fp32 form
+    RrmModelX2 rx2;
     // multi-band extension (zodi_multiband_*): this handle then carries band 0 and the shared parts
     int mb_bands = 0;
     MultiBandModel<double> mb64;
@@ -225,6 +227,7 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
                     build_kelsall_model(*d, m->k64);
     m->rrm_ok = d->n_temps <= kFastMaxTemps && d->n_nodes <= kFastMaxNodes && build_rrm_model(*d, m->m64, m->r64);
     if (m->rrm_ok) narrow_rrm(m->r64, m->m32, m->r32);
+    m->rrm_x2_ok = m->rrm_ok && build_rrm_x2(m->r64, m->r32, m->rx2);
     if (m->kelsall_ok) narrow_kelsall(m->k64, m->k32);
     const char* fg = std::getenv("ZODI_FORCE_GENERIC");
     m->force_generic = (fg && fg[0] == '1');
@@ -280,6 +283,12 @@ void flags_from_r(const zodi_model_s* m, double r_max, uint8_t* flags) {
     }
 }
 
+// Packed RRM kernel (one thread per PAIR of lines of sight, no lane split): once the pairs half-fill the
+// machine; smaller inputs take the scalar fused kernel with several lanes per line of sight.
+bool rrm_takes_packed(const zodi_model_s* m, int64_t n) {
+    return m->rrm_x2_ok && !m->no_x2 && n >= (int64_t)sm_count() * 1024;
+}
+
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     if (m->mb_bands > 0) {
@@ -295,6 +304,8 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
         return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }
     if (m->rrm_ok && !m->force_generic) {
+        if (precision == ZODI_FP32 && rrm_takes_packed(m, a.n))
+            return launch_rrm_packed(m->rx2, a, m->d_table32, m->d_nodes32, stream);
         if (precision == ZODI_FP32) return launch_rrm_f32(m->r32, a, m->d_table32, m->d_nodes32, stream);
         return launch_rrm_f64(m->r64, a, m->d_table64, m->d_nodes64, stream);
     }
@@ -1146,7 +1157,8 @@ int zodi_peer_rendezvous(int device, void* const* peer_flags, int32_t n_peers, i
 
 const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
     if (!m) return "";
-    if (m->rrm_ok && !m->force_generic) return "zodi_los_rrm_kernel";
+    if (m->rrm_ok && !m->force_generic)
+        return (precision == ZODI_FP32 && rrm_takes_packed(m, n)) ? "zodi_los_rrm_x2_kernel" : "zodi_los_rrm_kernel";
     if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";
     if (precision == ZODI_FP32 && !m->no_x2) return "zodi_los_kelsall_x2_kernel";
     return "zodi_los_kelsall_kernel";

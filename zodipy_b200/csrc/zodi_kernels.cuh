@@ -15,6 +15,7 @@
 #include "zodi_kelsall_x2.cuh"
 #include "zodi_multiband.cuh"
 #include "zodi_rrm.cuh"
+#include "zodi_rrm_x2.cuh"
 
 namespace zodi {
 
@@ -345,6 +346,48 @@ zodi_los_rrm_kernel(const __grid_constant__ RrmModel<Real> model,
                 store_out<Real>(args, ci, j, v);
         });
     if (!args.return_comps && active && sub == 0) store_out<Real>(args, 0, j, total);
+}
+
+// Packed-fp32 fused RRM kernel (zodi_rrm_x2.cuh): two lines of sight per thread (j and j + THREADS of the
+// CTA's block), large-N fp32 path of the RRM model.
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+zodi_los_rrm_x2_kernel(const __grid_constant__ RrmModelX2 model,
+                       const __grid_constant__ LaunchArgs args,
+                       const Pair<float>* __restrict__ g_table,
+                       const Pair<float>* __restrict__ g_nodes) {
+    __shared__ Pair<float> s_table[kFastMaxTemps];
+    __shared__ Pair<float> s_nodes[kFastMaxNodes];
+    for (int i = threadIdx.x; i < model.r.n_temps; i += blockDim.x) s_table[i] = g_table[i];
+    for (int i = threadIdx.x; i < model.r.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    const int64_t j0 = (int64_t)blockIdx.x * (2 * THREADS) + threadIdx.x, j1 = j0 + THREADS;
+    const bool act0 = j0 < args.n, act1 = j1 < args.n;
+    const int64_t jj0 = act0 ? j0 : args.n - 1, jj1 = act1 ? j1 : args.n - 1;
+    LosPre P[2];
+    RrmIntervals I[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int64_t jj = q ? jj1 : jj0;
+        double ux, uy, uz, ox, oy, oz, ex, ey;
+        load_direction(args, jj, ux, uy, uz);
+        load_positions(args, jj, true, ox, oy, oz, ex, ey);
+        rrm_pre(model, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask, P[q], I[q]);
+    }
+    float tot0 = 0.f, tot1 = 0.f;
+    integrate_rrm_x2(model, s_table, s_nodes, P[0], P[1], I[0], I[1], [&](int ci, float va, float vb) {
+        tot0 += va;
+        tot1 += vb;
+        if (args.return_comps) {
+            if (act0) store_out<float>(args, ci, j0, va);
+            if (act1) store_out<float>(args, ci, j1, vb);
+        }
+    });
+    if (!args.return_comps) {
+        if (act0) store_out<float>(args, 0, j0, tot0);
+        if (act1) store_out<float>(args, 0, j1, tot1);
+    }
 }
 
 // Multi-band kernel (zodi_multiband.cuh): NB bands of one Kelsall-family model per pass; output

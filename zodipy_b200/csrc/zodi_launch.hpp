@@ -45,6 +45,8 @@ cudaError_t launch_multiband_f64(const MultiBandModel<double>& MB, const LaunchA
 // fused RRM kernels (zodi_rrm.cuh)
 cudaError_t launch_rrm_f32(const RrmModel<float>& R, const LaunchArgs& a, const Pair<float>* tab,
                            const Pair<float>* nodes, cudaStream_t stream);
+cudaError_t launch_rrm_packed(const RrmModelX2& X, const LaunchArgs& a, const Pair<float>* tab, const Pair<float>* nodes,
+                              cudaStream_t stream);
 cudaError_t launch_rrm_f64(const RrmModel<double>& R, const LaunchArgs& a, const Pair<double>* tab,
                            const Pair<double>* nodes, cudaStream_t stream);
 

@@ -16,6 +16,18 @@ cudaError_t launch_rrm_L(const RrmModel<Real>& R, const LaunchArgs& a, const Pai
 }
 }  // namespace
 
+#if defined(ZODI_TU_IS_F32)
+// packed fp32 kernel: 128-thread CTAs, 8 per SM (64 registers)
+cudaError_t launch_rrm_packed(const RrmModelX2& X, const LaunchArgs& a, const Pair<float>* tab, const Pair<float>* nodes,
+                              cudaStream_t stream) {
+    constexpr int kT = 128;
+    const int64_t grid = (a.n + 2 * kT - 1) / (2 * kT);
+    zodi_los_rrm_x2_kernel<kT, 8><<<(unsigned)grid, kT, 0, stream>>>(X, a, tab, nodes);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+#endif
+
 #define ZODI_CAT2(a, b) a##b
 #define ZODI_CAT(a, b) ZODI_CAT2(a, b)
 

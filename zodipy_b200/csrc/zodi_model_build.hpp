@@ -10,6 +10,7 @@
 #include "zodi_device.cuh"
 #include "zodi_kelsall.cuh"
 #include "zodi_rrm.cuh"
+#include "zodi_rrm_x2.cuh"
 
 namespace zodi {
 
@@ -324,6 +325,29 @@ inline void narrow_rrm(const RrmModel<From>& a, const DevModel<To>& m, RrmModel<
         b.c[i] = m.comps[i];  // already narrowed by narrow_model()
     }
     b.f_cos0 = a.f_cos0; b.f_sin0 = a.f_sin0;
+}
+
+// Packed fp32 form (zodi_rrm_x2.cuh): the narrowed RRM block plus the ring / feature constants in the
+// KelsallModel layout the packed ring / feature loops read.  Returns false when ring and feature do not
+// share one temperature law (then the scalar fused kernel is used).
+inline bool build_rrm_x2(const RrmModel<double>& R64, const RrmModel<float>& R32, RrmModelX2& X) {
+    std::memset(&X, 0, sizeof(X));
+    if (R64.t_scale[R_RING] != R64.t_scale[R_FEATURE] || R64.mhd[R_RING] != R64.mhd[R_FEATURE]) return false;
+    X.r = R32;
+    KelsallModel<float>& K = X.rf;
+    K.n_comps = 6; K.n_nodes = R64.n_nodes; K.n_temps = R64.n_temps;
+    K.t_scale = (float)R64.t_scale[R_RING]; K.t_ofs = (float)R64.t_ofs; K.t_top = (float)R64.t_top;
+    K.mhd = (float)R64.mhd[R_RING];
+    const DevComp<double>&r = R64.c[R_RING], &f = R64.c[R_FEATURE];
+    K.rnx = (float)r.nx; K.rny = (float)r.ny; K.rnz = (float)r.nz;
+    K.r_R = (float)r.s[1]; K.r_c2 = (float)r.s[2]; K.r_c3 = (float)r.s[3];
+    K.fnx = (float)f.nx; K.fny = (float)f.ny; K.fnz = (float)f.nz;
+    K.f_R = (float)f.s[1]; K.f_c2 = (float)f.s[2]; K.f_c3 = (float)f.s[3]; K.f_theta0 = (float)f.s[4];
+    K.f_c5 = (float)f.s[5];
+    K.aB[4] = (float)(r.s[0] * R64.e1);  // A n_0 calibration
+    K.aB[5] = (float)(f.s[0] * R64.e1);
+    K.f_cos0 = R64.f_cos0; K.f_sin0 = R64.f_sin0;
+    return true;
 }
 
 // Not-a-knot cubic spline through uniformly or non-uniformly spaced knots, one axis: the same
