@@ -18,8 +18,23 @@ TOL_FP32 = 1e-5
 # eps / (R/delta_r)**20 > 1e-10, on components that are < 1e-9 of the total.  A floor of 1e-6 of the
 # total keeps those noise-dominated values from being compared digit for digit.
 COMP_FLOOR_FP64 = 1e-6
-# fp32: components are gated against max(|component|, |total|) (SURVEY.md 8(a) fp32 note).
+# fp32: components are gated against max(|component|, |total|) (SURVEY.md 8(a) fp32 note): the relaxed gate,
+# kept for the RRM model (hard density cut-offs decided in fp32) and for the random sweeps over extreme observers.
 COMP_FLOOR_FP32 = 1.0
+# fp32, Kelsall-family models on the committed fixtures and the Earth-bound fresh inputs: every component
+# within 1e-5 of max(|component|, 1 % of the total).  Measured on B200 (benchmarks/component_errors.py,
+# profiles/r2_component_errors_fp32.jsonl): cloud 2.1e-6, band1 1.8e-6, band2 8.7e-6, band3 1.8e-6, ring 4.8e-6,
+# feature 1.5e-6.  Components below 1 % of the total are limited by the fp32 representation of the node
+# positions (6e-8 AU against a band half-width of 0.035 AU, ring sigma_r = 0.025 AU): band2 reaches 1.9e-5 at a
+# floor of 0.1 %, 3.3e-5 at 0.01 %.
+COMP_FLOOR_FP32_KELSALL = 1e-2
+
+
+def comp_floor(precision, spec_kind):
+    """Per-component floor (fraction of the total) for a precision mode and model kind."""
+    if precision == "fp64":
+        return COMP_FLOOR_FP64
+    return COMP_FLOOR_FP32_KELSALL if spec_kind == "kelsall" else COMP_FLOOR_FP32
 
 
 @functools.lru_cache(maxsize=None)
