@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--shard", default="auto", choices=["auto", "contiguous", "cyclic"],
                     help="N>1 shard layout: contiguous (np.array_split rule) or block-cyclic "
                          "(load-balanced; default with the fused gather)")
+    ap.add_argument("--cyclic-block", type=int, default=0, help="block length of the block-cyclic layout "
+                                                                 "(default: zodipy_b200.sharding.CYCLIC_BLOCK)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations")
@@ -510,9 +512,10 @@ def run_b200(args):
     units_total = npix * ncomps * DEG
 
     # ---- inputs: pinned host copy (for e2e) and HBM-resident copy (for value) ----
+    cyc_block = args.cyclic_block or sharding.CYCLIC_BLOCK
     if cyclic:
         # block-cyclic shard: contiguous RING shards are latitude bands of unequal cost
-        shard_idx = sharding.cyclic_indices(npix, world, rank)
+        shard_idx = sharding.cyclic_indices(npix, world, rank, cyc_block)
         n_local = shard_idx.size
         u_host = torch.empty((3, n_local), dtype=torch.float64).pin_memory()
         for c0 in range(0, n_local, 1 << 22):
@@ -532,7 +535,7 @@ def run_b200(args):
     # N > 1: the kernel stores its slice into every rank's full map (fused all-gather over NVLink
     # peer memory); --gather nccl uses a separate NCCL all-gather instead.
     peer_map = sharding.PeerMap(npix, 1, out_dtype, local_rank,
-                                cyclic_block=sharding.CYCLIC_BLOCK if cyclic else 0) if fused else None
+                                cyclic_block=cyc_block if cyclic else 0) if fused else None
 
     def step():
         if fused:
@@ -601,7 +604,12 @@ def run_b200(args):
             check = sharding.allgather_map(out_local, npix)
             assert torch.equal(full, check), "assembled map differs from the all-gathered reference"
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))
+    kernel_ms_ranks = [kernel_ms]
     if world > 1:
+        mine = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        kernel_ms_ranks = [float(v) for v in every]  # rank imbalance of the integrator kernel
         t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, kernel_ms = float(t[0]), float(t[1])
@@ -792,15 +800,16 @@ def run_b200(args):
 
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(model.spec, args.nside)
 
-    shard_layout = ("block-cyclic, 65536-line blocks" if cyclic else "contiguous (np.array_split)") if world > 1 \
-        else "single GPU"
+    shard_layout = (f"block-cyclic, {cyc_block}-line blocks" if cyclic else "contiguous (np.array_split)") \
+        if world > 1 else "single GPU"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "f64",
         "data": "synthetic", "precision_mode": precision,
         "config": workload_config(args.nside),
-        "sharding": {"layout": shard_layout,
+        "sharding": {"layout": shard_layout, "kernel_ms_per_rank": kernel_ms_ranks,
+                     "rendezvous_us": 1e3 * (ms_per_step - kernel_ms),
                      "gather": ("kernel epilogue stores to all peers' maps (NVLink P2P)" if fused else
                                 "NCCL all-gather") if world > 1 else None},
         "pixels_per_s": npix / (ms_per_step * 1e-3),

@@ -748,3 +748,37 @@ def test_nprocesses_maps_to_devices(monkeypatch):
     ranked = zp.Model(zp.Quantity(25.0, "um"))
     ranked._use_processes(64)
     assert ranked._devices == [0]
+
+
+def test_multiband_outside_flags_are_per_model_component():
+    """A multi-band handle returns one row per BAND but reads 2 flag bytes per MODEL component: supplied
+    global flags must have shape (n_model_comps, 2) whatever the number of bands (3 bands, 6 components)."""
+    mb = zp.MultiBandModel([zp.Quantity(v, "um") for v in (12.0, 25.0, 60.0)], name="dirbe", precision="fp64")
+    dm = mb.device_model
+    assert dm.ncomps == 3 and dm.n_model_comps == 6
+    u = fibonacci_sphere(5000)
+    obs = EARTH_20220114 * 1.25  # outside the ring's outer cutoff sphere: early-out flags matter
+    flags = zp.Model(zp.Quantity(25.0, "um")).device_model.outside_flags(obs)
+    assert flags.shape == (6, 2) and flags.any()
+    auto = dm.evaluate(u, obs, EARTH_20220114)
+    given = dm.evaluate(u, obs, EARTH_20220114, outside_flags=flags)
+    np.testing.assert_array_equal(given, auto)
+    with pytest.raises(ValueError):
+        dm.evaluate(u, obs, EARTH_20220114, outside_flags=flags[:3])
+
+
+def test_generic_kernel_with_the_largest_tables_the_abi_admits():
+    """1024 table knots + 600 quadrature nodes need more dynamic shared memory than the 48 KB default next
+    to the static fp64 math tables: the generic kernel opts in instead of failing at launch."""
+    model = zp.Model(zp.Quantity(25.0, "um"), gauss_quad_degree=600)
+    spec = dict(model.spec)
+    t_old = np.asarray(spec["table"][0])
+    t_new = np.linspace(t_old[0], t_old[-1], 1024)
+    spec["table"] = np.array([t_new, np.interp(t_new, t_old, np.asarray(spec["table"][1]))])
+    dm = engine.DeviceModel(spec, 0)
+    assert dm.kernel_name == "zodi_los_generic_kernel"
+    u = fibonacci_sphere(300)
+    for precision, tol in (("fp64", TOL_FP64), ("fp32", TOL_FP32)):
+        got = dm.evaluate(u, EARTH_20220114, return_comps=True, precision=precision)
+        ref = oracle.evaluate(spec, u, EARTH_20220114, EARTH_20220114)
+        assert max_rel_total(got, ref) <= tol

@@ -259,3 +259,27 @@ def test_single_process_multi_device_tod_and_healpix(monkeypatch, observer):
     np.testing.assert_array_equal(hp, ref_hp)
     part = multi.evaluate_healpix(nside, obs, pix_range=(10, 77))
     np.testing.assert_array_equal(part, ref_hp.sum(axis=0)[10:77])
+
+
+def test_peer_slice_bounds_are_checked_before_launch():
+    """The kernel's peer stores go to remote GPU memory: a slice that does not fit the mapped maps must be
+    refused in Python (contiguous and block-cyclic layouts), whatever return_comps is."""
+    from types import SimpleNamespace
+
+    from zodipy_b200 import engine
+
+    check = engine.DeviceModel._check_peer_slice
+    contiguous = SimpleNamespace(cyclic=None, offset=100, n_total=1000)
+    check(None, contiguous, 900)
+    with pytest.raises(ValueError):
+        check(None, contiguous, 901)
+    n_total, parts, block = 1000, 3, 64
+    for rank in range(parts):
+        pm = SimpleNamespace(cyclic=(block, parts, rank), offset=0, n_total=n_total)
+        mine = sharding.cyclic_count(n_total, parts, rank, block)
+        check(None, pm, mine)
+        for wrong in (mine - 1, mine + 1, n_total):
+            if wrong != mine:
+                with pytest.raises(ValueError):
+                    check(None, pm, wrong)
+    assert sum(sharding.cyclic_count(n_total, parts, r, block) for r in range(parts)) == n_total
