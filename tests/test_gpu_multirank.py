@@ -139,6 +139,31 @@ def test_two_processes_one_gpu_bitwise(case_id, per_sample):
         np.testing.assert_array_equal(results[r]["gathered"], single)
 
 
+def test_fused_peer_store_two_processes_one_gpu():
+    """The fused gather on a 1-GPU box: two processes share cuda:0 (gloo for the set-up), each maps the
+    other's buffers through CUDA IPC, the kernels store into both maps and the flag rendezvous - spinning
+    kernels of two time-sliced processes - completes.  Same checks as the multi-GPU test (single evaluation,
+    repeated evaluations into one PeerMap, block-cyclic shards with on-device directions)."""
+    from helpers import golden_case
+    from zodipy_b200 import engine
+
+    case_id = "planck18_857"
+    case, a = golden_case(case_id)
+    dm1 = engine.DeviceModel(case["spec"], 0)
+    single = dm1.evaluate(a["u"], a["obs"], a["earth"], return_comps=True)
+    singles_scaled = [dm1.evaluate(a["u"], a["obs"] * s, a["earth"], return_comps=True,
+                                   outside_flags=sharding_flags(dm1, dm1.max_observer_radius(a["obs"]) * s))
+                      for s in WAR_SCALES]
+    hp_single = dm1.evaluate_healpix(16, a["obs"][:, :1], a["earth"][:, :1], return_comps=True)
+    results = _run(2, "gloo", case_id, False, "fp64", True)
+    for r in range(2):
+        np.testing.assert_array_equal(results[r]["fused"], single)
+        for k in range(len(WAR_SCALES)):
+            np.testing.assert_array_equal(results[r]["war"][k], singles_scaled[k])
+        np.testing.assert_array_equal(results[r]["cyclic_healpix"], hp_single)
+        np.testing.assert_allclose(results[r]["cyclic_array"], hp_single, rtol=1e-12)
+
+
 @pytest.mark.parametrize("case_id,per_sample", [("dirbe_25um_tod_straddle", True), ("planck18_857", False)])
 def test_fused_peer_store_equals_allgather(case_id, per_sample):
     import torch
