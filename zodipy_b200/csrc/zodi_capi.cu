@@ -468,7 +468,11 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
                   const zodi_lonlat_args* ll) {
     std::lock_guard<std::mutex> lock(m->ws_mutex);
     const int64_t n = a->n;
+    // 1 Mi-line chunks for large inputs; mid-size inputs (one device's shard of a map split over several
+    // GPUs) are cut into >= 12 chunks so that the first kernel does not wait for a long first upload and
+    // the last download is short (pipeline fill / drain)
     int64_t chunk = 1 << 20;
+    if (n < 12 * chunk) chunk = std::max<int64_t>(1 << 17, ((n + 11) / 12 + 0xFFFF) & ~(int64_t)0xFFFF);
     if (n < chunk) chunk = n;
     int rc = ensure_workspace(m, chunk);
     if (rc) return rc;

@@ -598,6 +598,14 @@ class MultiDeviceModel:
         self.models = [DeviceModel(spec, d) for d in devices]
         self.spec = spec
         self.ncomps = self.models[0].ncomps
+        self._pool = None  # worker threads, one per device, kept across calls
+
+    def _workers(self):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=len(self.models), thread_name_prefix="zodi-dev")
+        return self._pool
 
     def update(self, spec: dict) -> None:
         for m in self.models:
@@ -606,12 +614,13 @@ class MultiDeviceModel:
         self.ncomps = self.models[0].ncomps
 
     def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for m in self.models:
             m.close()
 
     def _run(self, n, obs, earth, return_comps, out, out_dtype, outside_flags, call):
-        from concurrent.futures import ThreadPoolExecutor
-
         from .sharding import split_bounds
 
         out_dtype = np.dtype(np.float64 if out_dtype is None else out_dtype)
@@ -639,8 +648,7 @@ class MultiDeviceModel:
             part = lambda a: a[:, lo:hi] if a.shape[1] == n and n > 1 else a  # noqa: E731
             call(m, lo, hi, part(obs), part(earth), out[..., lo:hi], flags)
 
-        with ThreadPoolExecutor(max_workers=len(shards)) as pool:
-            list(pool.map(work, shards))  # re-raises the first worker exception
+        list(self._workers().map(work, shards))  # re-raises the first worker exception
         return out
 
     def evaluate(self, u, obs, earth=None, *, return_comps: bool = False, precision: str = "fp64", out=None,
@@ -706,8 +714,6 @@ class MultiDeviceModel:
         per device by ``zodi_ephemeris_stats`` - which also stages each shard's times on its device - and
         combined on the host before any device integrates, so the result is bit-identical to one device.
         """
-        from concurrent.futures import ThreadPoolExecutor
-
         from .sharding import split_bounds
 
         if ephemeris.devices != self.devices:
@@ -739,28 +745,28 @@ class MultiDeviceModel:
             raise ValueError("this ephemeris carries observer knots; use observer='knots'")
         if observer not in ("earth", "semb-l2", "knots"):
             raise ValueError("observer must be 'earth', 'semb-l2' or 'knots'")
-        with ThreadPoolExecutor(max_workers=len(shards)) as pool:
-            for k, _, _ in shards:
-                ephemeris.parts[k].set_obs_scale(1.0)
-            stats = list(pool.map(lambda sh: ephemeris.parts[sh[0]].stats(t[sh[1]:sh[2]]), shards))
-            sum_r2 = float(np.sum([s[0] for s in stats]))
-            scale = 1.0
-            if observer == "semb-l2":
-                norm = float(np.sqrt(sum_r2))
-                scale = (norm + MEAN_DIST_TO_L2) / norm
-            r_max = max(s[2] for s in stats) if observer == "knots" else scale * max(s[1] for s in stats)
-            flags = spec_outside_flags(self.spec, r_max)
+        pool = self._workers()
+        for k, _, _ in shards:
+            ephemeris.parts[k].set_obs_scale(1.0)
+        stats = list(pool.map(lambda sh: ephemeris.parts[sh[0]].stats(t[sh[1]:sh[2]]), shards))
+        sum_r2 = float(np.sum([s[0] for s in stats]))
+        scale = 1.0
+        if observer == "semb-l2":
+            norm = float(np.sqrt(sum_r2))
+            scale = (norm + MEAN_DIST_TO_L2) / norm
+        r_max = max(s[2] for s in stats) if observer == "knots" else scale * max(s[1] for s in stats)
+        flags = spec_outside_flags(self.spec, r_max)
 
-            def work(sh):
-                k, lo, hi = sh
-                eph, m = ephemeris.parts[k], self.models[k]
-                eph.set_obs_scale(scale)
-                ll = None if lonlat is None else _LonLat(lon[lo:hi], lat[lo:hi], rot)
-                m.evaluate(None if ll is not None else u[:, lo:hi], ephemeris=eph, obstime=t[lo:hi], observer="prepared",
-                           lonlat=ll, return_comps=return_comps, precision=precision, out=out[..., lo:hi],
-                           out_dtype=out_dtype, outside_flags=flags)
+        def work(sh):
+            k, lo, hi = sh
+            eph, m = ephemeris.parts[k], self.models[k]
+            eph.set_obs_scale(scale)
+            ll = None if lonlat is None else _LonLat(lon[lo:hi], lat[lo:hi], rot)
+            m.evaluate(None if ll is not None else u[:, lo:hi], ephemeris=eph, obstime=t[lo:hi], observer="prepared",
+                       lonlat=ll, return_comps=return_comps, precision=precision, out=out[..., lo:hi],
+                       out_dtype=out_dtype, outside_flags=flags)
 
-            list(pool.map(work, shards))
+        list(pool.map(work, shards))
         return out
 
 
