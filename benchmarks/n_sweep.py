@@ -96,7 +96,7 @@ def main():
             units = n * model.ncomps * len(model.spec["points"])
             shapes = [(0, 0)]
             if args.shapes and "x2" in dm.kernel_name_for(n, args.precision):
-                shapes += [(lanes, th) for th in (256, 128, 64) for lanes in (1, 2, 4, 8)
+                shapes += [(lanes, th) for th in (256, 128) for lanes in (1, 2, 4, 8)
                            if n * lanes <= 2 * 148 * 1280 * 16]
             for lanes, threads in shapes:
                 for k, v in (("ZODI_X2_LANES", lanes), ("ZODI_X2_THREADS", threads)):

@@ -59,7 +59,7 @@ PackedShape pick_packed_shape(int64_t n, int n_nodes, int n_comps) {
     const char* et = std::getenv("ZODI_X2_THREADS");
     const int env_lanes = el ? std::atoi(el) : 0, env_threads = et ? std::atoi(et) : 0;
     PackedShape s;
-    s.threads = (env_threads == 64 || env_threads == 128 || env_threads == 256) ? env_threads : kPackedDefaultThreads;
+    s.threads = (env_threads == 128 || env_threads == 256) ? env_threads : kPackedDefaultThreads;
     if (env_lanes == 1 || env_lanes == 2 || env_lanes == 4 || env_lanes == 8) {
         s.lanes = env_lanes;
         return s;
@@ -73,12 +73,6 @@ PackedShape pick_packed_shape(int64_t n, int n_nodes, int n_comps) {
         const double thr = std::fmin(1.0, 1.25 * f / (f + 0.25));
         const double cost = (6.0 + loops * ((n_nodes + L - 1) / L)) * L / thr;
         if (L == 1 || cost < best) { best = cost; s.lanes = L; }
-    }
-    // few waves of CTAs (a shard of a sharded map): halve the CTA again so the tail of the launch - the last,
-    // partly filled wave - is half as long; 32 resident CTAs per SM are the hardware limit, 20 are used
-    if (!env_threads && s.threads == 128) {
-        const double waves = pairs * s.lanes / slots;
-        if (waves > 4.0 && waves < 48.0) s.threads = 64;
     }
     return s;
 }

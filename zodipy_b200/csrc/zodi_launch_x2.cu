@@ -10,9 +10,10 @@ constexpr int L = ZODI_TU_LANES;
 // 5 CTAs of 256 threads per SM (48 registers): cloud+bands only measured 5 % faster than 4 CTAs/SM (60
 // registers) and 0.4 % faster than 6 (40 registers); with the ring/feature loops 5 CTAs/SM is 0.8 % faster
 // than 4 (64 registers) - the spills it causes sit in the per-line-of-sight prologue / epilogue, not in the
-// node loops.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  128- and 64-thread
-// CTAs keep the same number of resident warps in 2x / 4x as many, shorter CTAs (shorter tail of a launch;
-// 64-thread CTAs for launches of fewer than ~40 waves, e.g. one rank's shard of a map sharded over 8 GPUs).
+// node loops.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  128-thread CTAs
+// keep the same number of resident warps in twice as many, half as long CTAs (shorter tail of a launch);
+// 64-thread CTAs measured the same again (profiles/r2_packed_cta_size_sweep.jsonl, r2_bench_n8_t128.json)
+// and were dropped.
 #ifndef ZODI_X2_CTAS_THERMAL
 #define ZODI_X2_CTAS_THERMAL 5
 #endif
@@ -36,7 +37,6 @@ cudaError_t launch_T(const KelsallModel<float>& K, const LaunchArgs& a, const Pa
 template <bool HAS_RF, bool SHARE13, bool SCATTER>
 cudaError_t launch_S(const KelsallModel<float>& K, const LaunchArgs& a, const Pair<float>* tab,
                      const Pair<float>* nodes, int threads, cudaStream_t stream) {
-    if (threads == 64) return launch_T<HAS_RF, SHARE13, SCATTER, 64>(K, a, tab, nodes, stream);
     return threads == 128 ? launch_T<HAS_RF, SHARE13, SCATTER, 128>(K, a, tab, nodes, stream)
                           : launch_T<HAS_RF, SHARE13, SCATTER, 256>(K, a, tab, nodes, stream);
 }

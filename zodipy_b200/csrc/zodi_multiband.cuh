@@ -54,7 +54,7 @@ ZODI_HD BandNode<Real> band_node(const KelsallModel<Real>& K, Real R_los, const 
     s.yh = M::fma_(R_los, G.uy, G.oy);
     s.zh = M::fma_(R_los, G.uz, G.oz);
     s.Rh2 = M::fma_(s.xh, s.xh, M::fma_(s.yh, s.yh, s.zh * s.zh));
-    const Real t = M::fma_(K.t_scale, M::exp2_(K.mhd * M::log2_(s.Rh2)), K.t_ofs);
+    const Real t = M::fma_(K.t_scale, M::exp2_bounded_(K.mhd * M::log2_(s.Rh2)), K.t_ofs);
     table_locate<Real>(t, K.t_top, s.idx, s.frac);
     s.th = Real(0);
     s.rh2inv = Real(0);

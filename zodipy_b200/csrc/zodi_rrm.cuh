@@ -51,7 +51,7 @@ ZODI_HD RrmNode<Real> rrm_node(const RrmModel<Real>& R, int slot, const Pair<Rea
     s.zh = M::fma_(R_los, G.uz, G.oz);
     s.R2 = M::fma_(s.xh, s.xh, M::fma_(s.yh, s.yh, s.zh * s.zh));
     s.lgR2 = M::log2_(s.R2);
-    const Real t = M::fma_(R.t_scale[slot], M::exp2_(R.mhd[slot] * s.lgR2), R.t_ofs);  // blackbody.py:30
+    const Real t = M::fma_(R.t_scale[slot], M::exp2_bounded_(R.mhd[slot] * s.lgR2), R.t_ofs);  // blackbody.py:30
     s.wB = nw.b * table_at<Real>(tab, t, R.t_top);                  // brightness.py:81
     return s;
 }
