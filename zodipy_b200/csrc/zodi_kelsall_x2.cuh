@@ -15,6 +15,12 @@
 
 #include "zodi_kelsall.cuh"
 
+#ifndef ZODI_X2_BAND_PRETEST
+#define ZODI_X2_BAND_PRETEST 1  // band skips decided before 1/R (see kelsall_group_a_x2); 0: round-1 flow (A/B)
+#endif
+#ifndef ZODI_X2_RF_FIRST
+#define ZODI_X2_RF_FIRST 1  // ring / feature loops before the cloud + bands loop (register pressure); 0: after (A/B)
+#endif
 #ifndef ZODI_X2_UNROLL
 #define ZODI_X2_UNROLL 1  // node-loop unroll factor of the packed cloud + bands loop (measured: see DESIGN.md)
 #endif
@@ -229,6 +235,15 @@ ZODI_HD Pair<float> lane_node(const Pair<float>* nodes, int n_nodes, int k0, int
     return nw;
 }
 
+// band_accumulate2 with the plane distance dot = n . X already formed and the skip already decided by the
+// caller (ZODI_X2_BAND_PRETEST): same operations on the lanes that are computed.
+ZODI_HD void band_accumulate2_dot(F2& acc, F2 wB, F2 dot, F2 rinv, F2 rinv_rad, float c3) {
+    const F2 sz = mul2(dot, rinv);
+    const F2 s2 = mul2(sz, sz), s4 = mul2(s2, s2), s6 = mul2(s4, s2);
+    const F2 n = mul2(mul2(ex2_neg2(s6), fma2(s4, c3, 1.0f)), rinv_rad);
+    acc = fma2(wB, n, acc);
+}
+
 // Group A (cloud + band1..3) for two lines of sight; lane `sub` of L takes nodes sub, sub + L, ...
 // emit(ci, partial_a, partial_b): partial quadrature sums times the half-range (the caller adds the
 // L partials of a line of sight).
@@ -265,8 +280,40 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
         const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
         const F2 n0 = ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
         // bands
-        const F2 rinv = rsq_2(Rh2);
         const F2 wB = mul2(B, nw.b);
+#if ZODI_X2_BAND_PRETEST
+        if (!SCATTER) {
+            // Decide the three band skips on (n . X)^2 > c R^2 (FMA pipe only) BEFORE forming 1/R: when every
+            // band of the (warp, node) is skipped - exp(-s^6) == 0 in all lanes - the MUFU.RSQ pair is dead
+            // too.  The threshold carries a 1e-5 margin over kS2Underflow, so a skipped band has s^2 > 5.02
+            // whatever the rounding of rsqrt; lanes in between are computed and get their exact 0 from ex2.
+            const F2 d1 = fma2(xh, K.bnx[0], fma2(yh, K.bny[0], mul2(zh, K.bnz[0])));
+            const F2 d2 = fma2(xh, K.bnx[1], fma2(yh, K.bny[1], mul2(zh, K.bnz[1])));
+            const F2 d3 = fma2(xh, K.bnx[2], fma2(yh, K.bny[2], mul2(zh, K.bnz[2])));
+            const F2 thr = mul2(Rh2, Math<float>::kS2Underflow * 1.00001f);
+            const F2 q1 = mul2(d1, d1), q2 = mul2(d2, d2), q3 = mul2(d3, d3);
+            const bool need1 = warp_any(q1.x <= thr.x || q1.y <= thr.y);
+            const bool need2 = warp_any(q2.x <= thr.x || q2.y <= thr.y);
+            const bool need3 = warp_any(q3.x <= thr.x || q3.y <= thr.y);
+            if (need1 || need2 || need3) {
+                const F2 rinv = rsq_2(Rh2);
+                F2 rr1 = rinv, rr2 = rinv, rr3 = rinv;
+                const F2 ymin = mul2(Rh2, by_min);
+                if (warp_any(ymin.x < Math<float>::kRadialOne || ymin.y < Math<float>::kRadialOne)) {
+                    if (need1 || (SHARE13 && need3)) band_radial2(Rh2, K.b_y[0], rinv, rr1);
+                    if (need2) band_radial2(Rh2, K.b_y[1], rinv, rr2);
+                    if (SHARE13) rr3 = rr1;
+                    else if (need3) band_radial2(Rh2, K.b_y[2], rinv, rr3);
+                }
+                if (need1) band_accumulate2_dot(a1, wB, d1, rinv, rr1, K.b_c3[0]);
+                if (need2) band_accumulate2_dot(a2, wB, d2, rinv, rr2, K.b_c3[1]);
+                if (need3) band_accumulate2_dot(a3, wB, d3, rinv, rr3, K.b_c3[2]);
+            }
+            a0 = fma2(wB, n0, a0);
+            continue;
+        }
+#endif
+        const F2 rinv = rsq_2(Rh2);
         F2 wF = f2(0.f);
         if (SCATTER) wF = mul2(scatter_term2(K, ux, uy, uz, xh, yh, zh, rinv), nw.b);  // rinv == 1/R_h (bands are Sun-centred)
         // 1 - 2^(-y^10) is exactly 1 for every band once R^2 * min(b_y) >= kRadialOne in all lanes (b_y > 0:

@@ -299,11 +299,26 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
             if (act1) store_out<float>(args, ci, j1, vb);
         }
     };
+#if ZODI_X2_RF_FIRST
+    // ring / feature first: during the cloud + bands loop only their four results stay live instead of the
+    // twelve interval / rotation values; components are still emitted (and summed) in model order
+    float ra = 0.f, rb = 0.f, fa = 0.f, fb = 0.f;
+    if (HAS_RF) {
+        kelsall_ring_x2<SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, [&](float a, float b) { ra = a; rb = b; });
+        kelsall_feature_x2<SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, [&](float a, float b) { fa = a; fb = b; });
+    }
+    kelsall_group_a_x2<SHARE13, SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, emit2);
+    if (HAS_RF) {
+        emit2(4, ra, rb);
+        emit2(5, fa, fb);
+    }
+#else
     kelsall_group_a_x2<SHARE13, SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, emit2);
     if (HAS_RF) {
         kelsall_ring_x2<SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, [&](float a, float b) { emit2(4, a, b); });
         kelsall_feature_x2<SCATTER, L>(model, s_table, s_nodes, P0, P1, sub, [&](float a, float b) { emit2(5, a, b); });
     }
+#endif
     if (!args.return_comps && sub == 0) {
         if (act0) store_out<float>(args, 0, j0, tot0);
         if (act1) store_out<float>(args, 0, j1, tot1);
