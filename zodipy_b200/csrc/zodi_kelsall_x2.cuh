@@ -297,17 +297,23 @@ ZODI_HD void kelsall_group_a_x2(const KelsallModel<float>& K, const Pair<float>*
             const bool need3 = warp_any(q3.x <= thr.x || q3.y <= thr.y);
             if (need1 || need2 || need3) {
                 const F2 rinv = rsq_2(Rh2);
-                F2 rr1 = rinv, rr2 = rinv, rr3 = rinv;
                 const F2 ymin = mul2(Rh2, by_min);
-                if (warp_any(ymin.x < Math<float>::kRadialOne || ymin.y < Math<float>::kRadialOne)) {
+                if (!warp_any(ymin.x < Math<float>::kRadialOne || ymin.y < Math<float>::kRadialOne)) {
+                    // common case: every radial cut-off factor is exactly 1 (separate code, so that no
+                    // register copies of 1/R are formed for it)
+                    if (need1) band_accumulate2_dot(a1, wB, d1, rinv, rinv, K.b_c3[0]);
+                    if (need2) band_accumulate2_dot(a2, wB, d2, rinv, rinv, K.b_c3[1]);
+                    if (need3) band_accumulate2_dot(a3, wB, d3, rinv, rinv, K.b_c3[2]);
+                } else {
+                    F2 rr1 = rinv, rr2 = rinv, rr3 = rinv;
                     if (need1 || (SHARE13 && need3)) band_radial2(Rh2, K.b_y[0], rinv, rr1);
                     if (need2) band_radial2(Rh2, K.b_y[1], rinv, rr2);
                     if (SHARE13) rr3 = rr1;
                     else if (need3) band_radial2(Rh2, K.b_y[2], rinv, rr3);
+                    if (need1) band_accumulate2_dot(a1, wB, d1, rinv, rr1, K.b_c3[0]);
+                    if (need2) band_accumulate2_dot(a2, wB, d2, rinv, rr2, K.b_c3[1]);
+                    if (need3) band_accumulate2_dot(a3, wB, d3, rinv, rr3, K.b_c3[2]);
                 }
-                if (need1) band_accumulate2_dot(a1, wB, d1, rinv, rr1, K.b_c3[0]);
-                if (need2) band_accumulate2_dot(a2, wB, d2, rinv, rr2, K.b_c3[1]);
-                if (need3) band_accumulate2_dot(a3, wB, d3, rinv, rr3, K.b_c3[2]);
             }
             a0 = fma2(wB, n0, a0);
             continue;
