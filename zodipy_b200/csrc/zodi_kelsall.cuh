@@ -117,6 +117,17 @@ ZODI_HD void band_accumulate(Real& accB, Real& accS, Real wB, Real wF, Real xh, 
     }
 }
 
+// band_accumulate with the plane distance dot = n . X already formed and the skip already decided by the
+// caller: same operations on the lanes that are computed.
+template <typename Real>
+ZODI_HD void band_accumulate_dot(Real& accB, Real wB, Real dot, Real rinv, Real rinv_rad, Real c3) {
+    using M = Math<Real>;
+    const Real sz = dot * rinv;
+    const Real s2 = sz * sz, s4 = s2 * s2, s6 = s4 * s2;
+    const Real n = (M::exp2_neg_(s6) * M::fma_(s4, c3, Real(1))) * rinv_rad;
+    accB = M::fma_(wB, n, accB);
+}
+
 // 1 - exp(-(R/delta_r)^20) with y = R^2 * log2e^(1/10) / delta_r^2  (y^10 = log2e * (R/delta_r)^20).
 // Beyond kRadialOne (R > ~1.2 delta_r: most of a line of sight that runs out to 5.2 AU) the term is
 // exactly 1; when the whole warp is there the power chain and the exponential are skipped.
@@ -179,8 +190,31 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
         const NodeSource<Real> s = node_source<Real, SCATTER>(K, tab, M::fma_(h, nw.a, mid), G.ux, G.uy,
                                                               G.uz, G.ox, G.oy, G.oz);
         // bands: centred on the Sun -> share R
-        const Real rinv = M::rsqrt_(s.Rh2);
         const Real wB = nw.b * s.B, wF = SCATTER ? nw.b * s.F : Real(0);
+        if (!SCATTER) {
+            // Band skips decided on (n . X)^2 > c R^2 BEFORE forming 1/R (see kelsall_group_a_x2): when every
+            // band of the (warp, node) is skipped the reciprocal square root is dead too.  The margin over
+            // kS2Underflow covers the rounding of rsqrt; lanes in between are computed and get an exact 0.
+            const Real d1 = M::fma_(s.xh, K.bnx[0], M::fma_(s.yh, K.bny[0], s.zh * K.bnz[0]));
+            const Real d2 = M::fma_(s.xh, K.bnx[1], M::fma_(s.yh, K.bny[1], s.zh * K.bnz[1]));
+            const Real d3 = M::fma_(s.xh, K.bnx[2], M::fma_(s.yh, K.bny[2], s.zh * K.bnz[2]));
+            const Real thr = s.Rh2 * (M::kS2Underflow * Real(1.00001));
+            const bool need1 = warp_any(d1 * d1 <= thr), need2 = warp_any(d2 * d2 <= thr), need3 = warp_any(d3 * d3 <= thr);
+            if (need1 || need2 || need3) {
+                const Real rinv = M::rsqrt_(s.Rh2);
+                Real rr1 = rinv, rr2 = rinv, rr3 = rinv;
+                if (warp_any(s.Rh2 * by_min < M::kRadialOne)) {
+                    if (need1 || (SHARE13 && need3)) rr1 = rinv * band_radial<Real>(s.Rh2, K.b_y[0]);
+                    if (need2) rr2 = rinv * band_radial<Real>(s.Rh2, K.b_y[1]);
+                    if (SHARE13) rr3 = rr1;
+                    else if (need3) rr3 = rinv * band_radial<Real>(s.Rh2, K.b_y[2]);
+                }
+                if (need1) band_accumulate_dot<Real>(aB1, wB, d1, rinv, rr1, K.b_c3[0]);
+                if (need2) band_accumulate_dot<Real>(aB2, wB, d2, rinv, rr2, K.b_c3[1]);
+                if (need3) band_accumulate_dot<Real>(aB3, wB, d3, rinv, rr3, K.b_c3[2]);
+            }
+        } else {
+        const Real rinv = M::rsqrt_(s.Rh2);
         // all radial cut-off factors are exactly 1 once R^2 min(b_y) >= kRadialOne in every lane (b_y > 0, the
         // products are monotonic in b_y): one vote then replaces the per-band ones and rinv * 1 is rinv
         if (!warp_any(s.Rh2 * by_min < M::kRadialOne)) {
@@ -194,6 +228,7 @@ ZODI_HD void kelsall_group_a(const KelsallModel<Real>& K, const Pair<Real>* tab,
             band_accumulate<Real, SCATTER>(aB1, aS1, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad1, K.bnx[0], K.bny[0], K.bnz[0], K.b_c3[0]);
             band_accumulate<Real, SCATTER>(aB2, aS2, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad2, K.bnx[1], K.bny[1], K.bnz[1], K.b_c3[1]);
             band_accumulate<Real, SCATTER>(aB3, aS3, wB, wF, s.xh, s.yh, s.zh, rinv, rinv * rad3, K.bnx[2], K.bny[2], K.bnz[2], K.b_c3[2]);
+        }
         }
         // cloud
         const Real xc = s.xh - K.cx0, yc = s.yh - K.cy0, zc = s.zh - K.cz0;
