@@ -299,12 +299,12 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
         // packed-fp32 kernels: every fp32 evaluation of a Kelsall-family model
         if (precision == ZODI_FP32 && !m->no_x2)
             return launch_kelsall_packed(m->k32, a, m->d_table32, m->d_nodes32,
-                                         pick_packed_shape(a.n, m->k32.n_nodes, m->k32.n_comps), stream);
+                                         pick_packed_shape(a.shape_n > 0 ? a.shape_n : a.n, m->k32.n_nodes, m->k32.n_comps), stream);
         if (precision == ZODI_FP32) return launch_kelsall_f32(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }
     if (m->rrm_ok && !m->force_generic) {
-        if (precision == ZODI_FP32 && rrm_takes_packed(m, a.n))
+        if (precision == ZODI_FP32 && rrm_takes_packed(m, a.shape_n > 0 ? a.shape_n : a.n))
             return launch_rrm_packed(m->rx2, a, m->d_table32, m->d_nodes32, stream);
         if (precision == ZODI_FP32) return launch_rrm_f32(m->r32, a, m->d_table32, m->d_nodes32, stream);
         return launch_rrm_f64(m->r64, a, m->d_table64, m->d_nodes64, stream);
@@ -514,6 +514,7 @@ int evaluate_host(zodi_model_s* m, const zodi_eval_args* a, uint32_t mask, const
                                        cudaMemcpyHostToDevice, s.stream));
         LaunchArgs la;
         la.n = cn;
+        la.shape_n = n;
         la.u = d_u; la.u_stride = m->ws_chunk;
         la.obs = d_obs; la.obs_stride = m->ws_chunk; la.obs_per_sample = obs_ps;
         la.earth = d_earth; la.earth_stride = m->ws_chunk; la.earth_per_sample = earth_ps;
@@ -662,6 +663,7 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
 
     LaunchArgs la;
     la.n = a->n;
+    la.shape_n = a->n;
     la.u = a->u; la.u_stride = a->u_stride;
     la.obs = a->obs; la.obs_stride = a->obs_stride; la.obs_per_sample = (a->n_obs == a->n && a->n > 1);
     la.earth = a->earth; la.earth_stride = a->earth_stride;

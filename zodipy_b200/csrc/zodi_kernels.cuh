@@ -28,6 +28,10 @@ constexpr int kPackedDefaultThreads = ZODI_X2_DEFAULT_THREADS;  // CTA size of t
 // Launch-time arguments (plain pointers; device memory).
 struct LaunchArgs {
     int64_t n;
+    // lines of sight of the whole C-ABI call this launch belongs to (host-memory calls are cut into
+    // chunks): the launch shape (lanes per line of sight) is chosen from THIS number, so that the summation
+    // order of the lane partials - and with it the result, bit for bit - does not depend on the chunking
+    int64_t shape_n;
     const double* u;      int64_t u_stride;
     const double* obs;    int64_t obs_stride;   int obs_per_sample;    // 0: one observer
     const double* earth;  int64_t earth_stride; int earth_per_sample;

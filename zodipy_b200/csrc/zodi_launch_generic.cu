@@ -31,7 +31,7 @@ cudaError_t ZODI_CAT(launch_generic_, ZODI_TU_SUFFIX)(const DevModel<ZODI_TU_REA
                                                       const Pair<ZODI_TU_REAL>* tab, const Pair<ZODI_TU_REAL>* nodes,
                                                       cudaStream_t stream) {
     using Real = ZODI_TU_REAL;
-    switch (pick_lanes(a.n, M.n_nodes)) {
+    switch (pick_lanes(a.shape_n > 0 ? a.shape_n : a.n, M.n_nodes)) {
         case 1: return launch_generic_L<Real, 1>(M, a, tab, nodes, stream);
         case 2: return launch_generic_L<Real, 2>(M, a, tab, nodes, stream);
         case 4: return launch_generic_L<Real, 4>(M, a, tab, nodes, stream);

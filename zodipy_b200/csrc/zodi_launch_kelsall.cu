@@ -21,7 +21,7 @@ cudaError_t launch_kelsall_L(const KelsallModel<Real>& K, const LaunchArgs& a, c
 template <typename Real, bool HAS_RF, bool SCATTER, bool SHARE13>
 cudaError_t launch_kelsall_RSS(const KelsallModel<Real>& K, const LaunchArgs& a, const Pair<Real>* tab,
                                const Pair<Real>* nodes, cudaStream_t stream) {
-    if (pick_lanes(a.n, K.n_nodes) == 1)
+    if (pick_lanes(a.shape_n > 0 ? a.shape_n : a.n, K.n_nodes) == 1)
         return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 1>(K, a, tab, nodes, stream);
     return launch_kelsall_L<Real, HAS_RF, SCATTER, SHARE13, 8>(K, a, tab, nodes, stream);
 }

@@ -35,7 +35,7 @@ cudaError_t ZODI_CAT(launch_rrm_, ZODI_TU_SUFFIX)(const RrmModel<ZODI_TU_REAL>& 
                                                   const Pair<ZODI_TU_REAL>* tab, const Pair<ZODI_TU_REAL>* nodes,
                                                   cudaStream_t stream) {
     using Real = ZODI_TU_REAL;
-    switch (pick_lanes(a.n, R.n_nodes)) {
+    switch (pick_lanes(a.shape_n > 0 ? a.shape_n : a.n, R.n_nodes)) {
         case 1: return launch_rrm_L<Real, 1>(R, a, tab, nodes, stream);
         case 2: return launch_rrm_L<Real, 2>(R, a, tab, nodes, stream);
         case 4: return launch_rrm_L<Real, 4>(R, a, tab, nodes, stream);
