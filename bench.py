@@ -555,7 +555,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # clocks / throttle reasons are sampled (nvidia-smi, 20 ms period) from before the warm-up until
-    # >= 0.6 s of the same launches after the timed steps: the timed region itself lasts only tens of ms
+    # 1.5 s of the same launches after the timed steps: the timed region itself lasts only tens of ms
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -614,7 +614,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, kernel_ms = float(t[0]), float(t[1])
     ms_per_step = elapsed_ms / args.steps
-    for _ in range(int(np.ceil(600.0 / max(ms_per_step, 1e-3)))):  # same count on every rank (elapsed_ms is reduced)
+    # the timed region lasts tens of ms: keep the same launches going for 1.5 s so that nvidia-smi (one query
+    # takes ~40 ms whatever -lms says) delivers >= 20 samples under load; same count on every rank
+    for _ in range(int(np.ceil(1500.0 / max(ms_per_step, 1e-3)))):
         step()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -22,10 +22,6 @@
 
 #include "zodi_device.cuh"
 
-#ifndef ZODI_CLOUD_LOGFORM
-#define ZODI_CLOUD_LOGFORM 1  // fp32 cloud density from logarithms below the break (cloud_density); 0: A/B
-#endif
-
 namespace zodi {
 
 template <typename Real>
@@ -49,7 +45,6 @@ struct KelsallModel {
     // cloud (number_density.py:47-73)
     Real cx0, cy0, cz0, cnx, cny, cnz;
     Real c_mu, c_inv2mu, c_halfmu, c_mha, c_mbl, c_gamma;
-    Real c_mu2, c_lg_inv2mu;  // mu^2, log2(1 / (2 mu))
     // bands (number_density.py:76-110); normals pre-scaled by log2e^(1/6) / delta_zeta
     Real bnx[3], bny[3], bnz[3];
     Real b_c3[3];  // 1 / (v * log2e^(2/3))
@@ -149,26 +144,17 @@ ZODI_HD Real band_radial(Real Rh2, Real by) {
 }
 
 // Cloud density without its amplitude: Rc^-alpha exp(-beta g^gamma), g = zeta^2 / (2 mu) below the break
-// zeta = |Z_c| / R_c < mu and zeta - mu / 2 above it (number_density.py:69-73).  double: literally.  float:
-// lanes below the break (decided on Z_c^2 < mu^2 R_c^2) form lg2 g = 2 lg2|Z_c| - lg2 R_c^2 + lg2(1 / 2mu)
-// from logarithms - lg2 R_c^2 is needed for the radial power law anyway - so a warp whose lanes are all
-// below the break never forms 1 / R_c (4 instead of 5 MUFU); the choice depends on the lane's own data only.
+// zeta = |Z_c| / R_c < mu and zeta - mu / 2 above it (number_density.py:69-73).
+// (Tried and dropped, profiles/r2_ab_cloud_logform.jsonl: lg2 g = 2 lg2|Z_c| - lg2 R_c^2 - lg2 2mu for lanes
+// below the break, which spares warps that are entirely below it the reciprocal square root - 4 instead of
+// 5 MUFU - measured 6 % SLOWER: two more votes and the mixed warps cost more than the MUFU pair saves.)
 template <typename Real>
 ZODI_HD Real cloud_density(const KelsallModel<Real>& K, Real Rc2, Real Zc) {
     using M = Math<Real>;
-    if (sizeof(Real) == sizeof(double) || !ZODI_CLOUD_LOGFORM) {
-        const Real zeta = M::abs_(Zc) * M::rsqrt_(Rc2);
-        const Real g = (zeta < K.c_mu) ? zeta * zeta * K.c_inv2mu : zeta - K.c_halfmu;
-        const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
-        return M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
-    }
-    const Real lgRc2 = M::log2_(Rc2);
-    const bool low = Zc * Zc < Rc2 * K.c_mu2;
-    Real lg_lo = Real(0), lg_hi = Real(0);
-    if (warp_any(low)) lg_lo = M::fma_(M::log2_(M::abs_(Zc)), Real(2), K.c_lg_inv2mu) + (-lgRc2);
-    if (warp_any(!low)) lg_hi = M::log2_(M::mul_(M::abs_(Zc), M::rsqrt_(Rc2)) - K.c_halfmu);  // product rounded (no fma)
-    const Real gp = M::exp2_((low ? lg_lo : lg_hi) * K.c_gamma);
-    return M::exp2_(M::fma_(lgRc2, K.c_mha, gp * K.c_mbl));
+    const Real zeta = M::abs_(Zc) * M::rsqrt_(Rc2);
+    const Real g = (zeta < K.c_mu) ? zeta * zeta * K.c_inv2mu : zeta - K.c_halfmu;
+    const Real gp = M::exp2_(K.c_gamma * M::log2_(g));
+    return M::exp2_(M::fma_(K.c_mha, M::log2_(Rc2), K.c_mbl * gp));
 }
 
 // Per-line-of-sight quantities shared by the component groups (prologue in double).

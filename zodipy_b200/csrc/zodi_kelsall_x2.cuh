@@ -235,33 +235,13 @@ ZODI_HD Pair<float> lane_node(const Pair<float>* nodes, int n_nodes, int k0, int
     return nw;
 }
 
-// Cloud density without its amplitude, Rc^-alpha exp(-beta g^gamma) (number_density.py:69-73), for both
-// halves: cloud_density<float>() of zodi_kelsall.cuh.  Lanes below the break (zeta < mu, decided on
-// Z_c^2 < mu^2 R_c^2) take lg2 g from lg2 |Z_c| and the lg2 R_c^2 that the radial power law needs anyway, so a
-// warp whose lanes are all there never forms 1 / R_c: 4 instead of 5 MUFU per line of sight and node.
+// cloud_density<float>() for both halves.
 ZODI_HD F2 cloud_density2(const KelsallModel<float>& K, F2 Rc2, F2 Zc) {
-#if !ZODI_CLOUD_LOGFORM
-    {
-        const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
-        const F2 g_in = mul2(mul2(zeta, zeta), K.c_inv2mu), g_out = add2(zeta, -K.c_halfmu);
-        const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
-        const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
-        return ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
-    }
-#endif
-    const F2 lgRc2 = lg2_2(Rc2);
-    const F2 Z2 = mul2(Zc, Zc), lim = mul2(Rc2, K.c_mu2);
-    const bool low_x = Z2.x < lim.x, low_y = Z2.y < lim.y;
-    F2 lg_lo = f2(0.f), lg_hi = f2(0.f);
-    if (warp_any(low_x || low_y))
-        lg_lo = add2(fma2(lg2_2(f2(fabsf(Zc.x), fabsf(Zc.y))), 2.0f, K.c_lg_inv2mu), f2(-lgRc2.x, -lgRc2.y));
-    if (warp_any(!low_x || !low_y)) {
-        const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
-        lg_hi = lg2_2(add2(zeta, -K.c_halfmu));
-    }
-    const F2 lg_g = f2(low_x ? lg_lo.x : lg_hi.x, low_y ? lg_lo.y : lg_hi.y);
-    const F2 gp = ex2_2(mul2(lg_g, K.c_gamma));
-    return ex2_2(fma2(lgRc2, K.c_mha, mul2(gp, K.c_mbl)));
+    const F2 zeta = mul2(f2(fabsf(Zc.x), fabsf(Zc.y)), rsq_2(Rc2));
+    const F2 g_in = mul2(mul2(zeta, zeta), K.c_inv2mu), g_out = add2(zeta, -K.c_halfmu);
+    const F2 g = f2(zeta.x < K.c_mu ? g_in.x : g_out.x, zeta.y < K.c_mu ? g_in.y : g_out.y);
+    const F2 gp = ex2_2(mul2(lg2_2(g), K.c_gamma));
+    return ex2_2(fma2(lg2_2(Rc2), K.c_mha, mul2(gp, K.c_mbl)));
 }
 
 // band_accumulate2 with the plane distance dot = n . X already formed and the skip already decided by the

@@ -232,7 +232,6 @@ inline bool build_kelsall_model(const zodi_model_desc& d, KelsallModel<double>& 
     K.cnx = c[0].sin_Omega * c[0].sin_i; K.cny = -c[0].cos_Omega * c[0].sin_i; K.cnz = c[0].cos_i;
     K.c_mu = c[0].shape[4]; K.c_inv2mu = 1.0 / (2.0 * c[0].shape[4]); K.c_halfmu = 0.5 * c[0].shape[4];
     K.c_mha = -0.5 * c[0].shape[1]; K.c_mbl = -c[0].shape[2] * kLog2e; K.c_gamma = c[0].shape[3];
-    K.c_mu2 = c[0].shape[4] * c[0].shape[4]; K.c_lg_inv2mu = std::log2(1.0 / (2.0 * c[0].shape[4]));
     // bands: n_0, delta_zeta_rad, v, p, delta_r
     const double l6 = std::pow(kLog2e, 1.0 / 6.0), l23 = std::pow(kLog2e, 2.0 / 3.0),
                  l10 = std::pow(kLog2e, 0.1);
@@ -271,7 +270,7 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     for (int i = 0; i < kPhaseTerms; ++i) ZN(phase_poly[i]);
     for (int i = 0; i < 6; ++i) { ZN(aB[i]); ZN(aS[i]); }
     ZN(cx0); ZN(cy0); ZN(cz0); ZN(cnx); ZN(cny); ZN(cnz);
-    ZN(c_mu); ZN(c_inv2mu); ZN(c_halfmu); ZN(c_mha); ZN(c_mbl); ZN(c_gamma); ZN(c_mu2); ZN(c_lg_inv2mu);
+    ZN(c_mu); ZN(c_inv2mu); ZN(c_halfmu); ZN(c_mha); ZN(c_mbl); ZN(c_gamma);
     for (int i = 0; i < 3; ++i) { ZN(bnx[i]); ZN(bny[i]); ZN(bnz[i]); ZN(b_c3[i]); ZN(b_y[i]); }
     ZN(rnx); ZN(rny); ZN(rnz); ZN(r_R); ZN(r_c2); ZN(r_c3);
     ZN(fnx); ZN(fny); ZN(fnz); ZN(f_R); ZN(f_c2); ZN(f_c3); ZN(f_c5); ZN(f_theta0);
