@@ -12,6 +12,7 @@
 #include "../../zodipy_b200/csrc/zodi_model_build.hpp"
 #include "../../zodipy_b200/csrc/zodi_kelsall_x2.cuh"
 #include "../../zodipy_b200/csrc/zodi_rrm_x2.cuh"
+#include "../../zodipy_b200/csrc/zodi_multiband_x2.cuh"
 
 using namespace zodi;
 
@@ -238,6 +239,87 @@ extern "C" int zodi_emu_evaluate_mode(const zodi_model_desc* d, int precision, i
         run_kelsall<double>(k64, t64, n64, n, u, obs, n_obs, earth, n_earth, flags, lanes, out);
     }
     return 1;
+}
+
+// Multi-band routines (zodi_multiband.cuh / zodi_multiband_x2.cuh): out is (n_bands, n), component-summed.
+// packed = 0: scalar routine (fp64 or fp32); 1: packed fp32 routine with the knot-major table rows the kernel
+// stages.  Returns the padded band count of the instance that ran, -1 when the descriptors are not eligible.
+template <typename Real, int NB>
+static void run_multiband(const MultiBandModel<Real>& MB, const std::vector<Pair<Real>>& tabs,
+                          const std::vector<Pair<Real>>& nodes, int64_t n, const double* u, const double* obs,
+                          int64_t n_obs, const double* earth, int64_t n_earth, uint32_t mask, double* out) {
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+        auto emit = [&](int b, Real v) { if (b < MB.n_bands) out[b * n + j] = (double)v; };
+#define ZMB(RF, SC) integrate_kelsall_multiband<Real, NB, RF, SC>(MB, tabs.data(), nodes.data(), u[j], u[n + j], \
+        u[2 * n + j], obs[jo], obs[n_obs + jo], obs[2 * n_obs + jo], earth[je], earth[n_earth + je], mask, 0, 1, emit)
+        if (MB.base.n_comps == 6) { if (MB.base.scatter) ZMB(true, true); else ZMB(true, false); }
+        else { if (MB.base.scatter) ZMB(false, true); else ZMB(false, false); }
+#undef ZMB
+    }
+}
+
+template <int NB>
+static void run_multiband_x2(const MultiBandModel<float>& MB, const std::vector<Pair<float>>& tabs,
+                             const std::vector<Pair<float>>& nodes, int64_t n, const double* u, const double* obs,
+                             int64_t n_obs, const double* earth, int64_t n_earth, uint32_t mask, double* out) {
+    constexpr int kRow = MbRows<NB>::kRow;
+    const int nt = MB.base.n_temps;
+    // the kernel's staging loop: knot-major rows, bands past n_bands zero
+    std::vector<Pair<float>> rows_store((size_t)nt * kRow + 2, Pair<float>{0.f, 0.f});
+    Pair<float>* rows = rows_store.data();
+    if (reinterpret_cast<uintptr_t>(rows) % 16) ++rows;  // BandPair reads are 16-byte aligned
+    for (int i = 0; i < nt * kRow; ++i) {
+        const int knot = i / kRow, b = i - knot * kRow;
+        rows[i] = b < MB.n_bands ? tabs[(size_t)b * nt + knot] : Pair<float>{0.f, 0.f};
+    }
+    for (int64_t j0 = 0; j0 < n; j0 += 2) {
+        const int64_t jj[2] = {j0, j0 + 1 < n ? j0 + 1 : j0};
+        LosPre P[2];
+        for (int q = 0; q < 2; ++q) {
+            const int64_t j = jj[q], jo = n_obs == n ? j : 0, je = n_earth == n ? j : 0;
+            if (MB.base.n_comps == 6)
+                P[q] = los_pre<true>(MB.base, u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo],
+                                     obs[2 * n_obs + jo], earth[je], earth[n_earth + je], mask);
+            else
+                P[q] = los_pre<false>(MB.base, u[j], u[n + j], u[2 * n + j], obs[jo], obs[n_obs + jo],
+                                      obs[2 * n_obs + jo], earth[je], earth[n_earth + je], mask);
+        }
+        auto emit = [&](int b, float va, float vb) {
+            if (b < MB.n_bands) { out[b * n + jj[1]] = (double)vb; out[b * n + jj[0]] = (double)va; }
+        };
+#define ZMB(RF, SC) integrate_multiband_x2<NB, RF, SC>(MB, rows, nodes.data(), P[0], P[1], emit)
+        if (MB.base.n_comps == 6) { if (MB.base.scatter) ZMB(true, true); else ZMB(true, false); }
+        else { if (MB.base.scatter) ZMB(false, true); else ZMB(false, false); }
+#undef ZMB
+    }
+}
+
+extern "C" int zodi_emu_multiband(const zodi_model_desc* descs, int n_bands, int precision, int packed, int64_t n,
+                                  const double* u, const double* obs, int64_t n_obs, const double* earth,
+                                  int64_t n_earth, const uint8_t* flags, double* out) {
+    MultiBandModel<double> MB;
+    MultiBandModel<float> MF;
+    std::vector<Pair<double>> t64, n64, tb;
+    std::vector<Pair<float>> t32, n32, tbf;
+    if (n_bands < 1 || n_bands > kMaxBands || build_multiband_model(descs, n_bands, MB, MF, t64, t32) >= 0) return -1;
+    build_pairs(descs[0], tb, n64, tbf, n32);
+    uint32_t mask = 0;
+    for (int c = 0; c < MB.base.n_comps; ++c) {
+        if (flags[2 * c]) mask |= 1u << (2 * c);
+        if (flags[2 * c + 1]) mask |= 1u << (2 * c + 1);
+    }
+#define ZNB(NB)                                                                                                  \
+    do {                                                                                                         \
+        if (precision != ZODI_FP32) run_multiband<double, NB>(MB, t64, n64, n, u, obs, n_obs, earth, n_earth, mask, out); \
+        else if (packed) run_multiband_x2<NB>(MF, t32, n32, n, u, obs, n_obs, earth, n_earth, mask, out);         \
+        else run_multiband<float, NB>(MF, t32, n32, n, u, obs, n_obs, earth, n_earth, mask, out);                 \
+    } while (0)
+    if (MB.n_bands_padded == 4) ZNB(4);
+    else if (MB.n_bands_padded == 8) ZNB(8);
+    else ZNB(16);
+#undef ZNB
+    return MB.n_bands_padded;
 }
 
 // Not-a-knot cubic spline coefficients (the routine zodi_ephemeris_create uses), scipy layout

@@ -191,3 +191,77 @@ def test_fused_peer_store_equals_allgather(case_id, per_sample):
         np.testing.assert_array_equal(results[r]["cyclic_healpix"], hp_single)
         # directions from the host pix2vec differ from the device routine in the last ulp
         np.testing.assert_allclose(results[r]["cyclic_array"], hp_single, rtol=1e-12)
+
+
+def _worker_persistent(rank, world, port, backend, nside, name, x, unit, queue):
+    """fp32 map large enough for the persistent-tile form of the packed kernel (peer stores), three evaluations
+    back to back into one double-buffered PeerMap: the tile counters reset themselves between launches."""
+    import torch
+    import torch.distributed as dist
+
+    import zodipy_b200 as zp
+    from zodipy_b200 import sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev_index = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dm = zp.Model(zp.Quantity(x, unit), name=name, precision="fp32", device=dev_index).device_model
+        npix = 12 * nside * nside
+        out = {}
+        for return_comps in (False, True):
+            pm = sharding.PeerMap(npix, dm.ncomps if return_comps else 1, np.float32, dev_index, cyclic_block=4096)
+            maps = []
+            for scale in (1.0, 1.001, 1.0):
+                dm.evaluate_healpix(nside, EARTH * scale, EARTH, return_comps=return_comps, precision="fp32",
+                                    out_dtype=np.float32, peer_map=pm)
+                maps.append(pm.finish().cpu().numpy().copy())
+            assert not pm.timed_out()
+            dist.barrier()
+            pm.close()
+            out[return_comps] = maps
+        queue.put((rank, out))
+    except Exception as err:
+        queue.put((rank, err))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])
+
+
+@pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um")])
+def test_persistent_tiles_with_peer_stores(name, x, unit):
+    """Sharded fp32 map through the persistent-tile packed kernel == the one-launch single-device map, bit for
+    bit, on every rank and for repeated evaluations (2 processes on one GPU, or one per GPU when there are 2)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    import zodipy_b200 as zp
+
+    nside = 512  # 1.57 M lines of sight per rank = 6144 tiles > the 1480 resident CTAs
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    dm1 = zp.Model(zp.Quantity(x, unit), name=name, precision="fp32").device_model
+    singles = {rc: [dm1.evaluate_healpix(nside, EARTH * s, EARTH, return_comps=rc, precision="fp32",
+                                         out_dtype=np.float32) for s in (1.0, 1.001)] for rc in (False, True)}
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_persistent, args=(r, 2, port, backend, nside, name, x, unit, queue))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for r, v in results.items():
+        assert not isinstance(v, Exception), f"rank {r}: {v!r}"
+        for rc in (False, True):
+            for got, want in zip(v[rc], (singles[rc][0], singles[rc][1], singles[rc][0])):
+                np.testing.assert_array_equal(got.reshape(want.shape), want)

@@ -643,6 +643,64 @@ def test_multiband_equals_per_band_models(name, xs, unit, precision):
                                rtol=1e-12 if precision == "fp64" else 3e-6)
 
 
+@pytest.mark.parametrize("name,xs,unit", [
+    ("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um"),  # NB = 16, scattering in 3 bands
+    ("planck18", [100.0, 143.0, 217.0, 353.0, 545.0, 857.0], "GHz"),                # NB = 8, four components
+    ("dirbe", [25.0, 60.0, 100.0], "um"),                                             # NB = 4
+])
+def test_multiband_packed_kernel(name, xs, unit, monkeypatch):
+    """Packed multi-band kernel (two lines of sight per thread; taken once the pairs fill the machine): equals
+    the per-band single-band evaluations and the oracle, odd count (padded last pair), host == device memory,
+    and the scalar multi-band kernel (ZODI_NO_X2) within fp32 rounding."""
+    import torch
+
+    n = 60001
+    u = fibonacci_sphere(n)
+    mb = zp.MultiBandModel([zp.Quantity(x, unit) for x in xs], name=name, precision="fp32")
+    assert mb.device_model.kernel_name_for(n, "fp32") == "zodi_los_multiband_x2_kernel"
+    assert mb.device_model.kernel_name_for(6000, "fp32") == "zodi_los_multiband_kernel"
+    assert mb.device_model.kernel_name_for(n, "fp64") == "zodi_los_multiband_kernel"
+    got = mb.evaluate_xyz(u, EARTH_20220114)
+    assert got.shape == (len(xs), n) and np.isfinite(got).all()
+    sel = np.r_[np.arange(0, n, 61), n - 1]
+    for b, band in enumerate(mb.bands):
+        single = band.evaluate_xyz(u, EARTH_20220114)
+        np.testing.assert_allclose(got[b], single, rtol=3e-6)
+        ref = oracle.evaluate(band.spec, u[:, sel], EARTH_20220114, EARTH_20220114).sum(axis=0)
+        assert np.max(np.abs(got[b, sel] - ref) / np.abs(ref)) <= TOL["fp32"][0], xs[b]
+    dev = torch.device("cuda:0")
+    got_dev = mb.evaluate_xyz(torch.as_tensor(u, device=dev), torch.as_tensor(EARTH_20220114, device=dev))
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), got)
+    monkeypatch.setenv("ZODI_NO_X2", "1")
+    scalar = zp.MultiBandModel([zp.Quantity(x, unit) for x in xs], name=name, precision="fp32")
+    assert scalar.device_model.kernel_name_for(n, "fp32") == "zodi_los_multiband_kernel"
+    np.testing.assert_allclose(got, scalar.evaluate_xyz(u, EARTH_20220114), rtol=3e-6)
+
+
+@pytest.mark.parametrize("name,x,unit", [("planck18", 857.0, "GHz"), ("dirbe", 25.0, "um"), ("dirbe", 1.25, "um")])
+def test_persistent_tiles_equal_one_tile_per_cta(name, x, unit, monkeypatch):
+    """ZODI_X2_PERSIST=2: the packed kernel as a machine-sized grid whose CTAs claim tiles from a counter (the
+    form taken with peer stores) == the default one-tile-per-CTA launch, bit for bit; the counters reset
+    themselves, so repeated and interleaved calls keep working; small maps fall back to the plain grid."""
+    nside = 256  # 3072 tiles > 1480 resident CTAs
+    plain = zp.Model(zp.Quantity(x, unit), name=name, precision="fp32")
+    want = plain.evaluate_healpix(nside, EARTH_20220114, out_dtype=np.float32)
+    want_c = plain.device_model.evaluate_healpix(nside, EARTH_20220114, return_comps=True, precision="fp32",
+                                                 out_dtype=np.float32)
+    small = plain.evaluate_healpix(32, EARTH_20220114, out_dtype=np.float32)
+    monkeypatch.setenv("ZODI_X2_PERSIST", "2")
+    pers = zp.Model(zp.Quantity(x, unit), name=name, precision="fp32")
+    for _ in range(3):
+        np.testing.assert_array_equal(pers.evaluate_healpix(nside, EARTH_20220114, out_dtype=np.float32), want)
+        np.testing.assert_array_equal(
+            pers.device_model.evaluate_healpix(nside, EARTH_20220114, return_comps=True, precision="fp32",
+                                               out_dtype=np.float32), want_c)
+        np.testing.assert_array_equal(pers.evaluate_healpix(32, EARTH_20220114, out_dtype=np.float32), small)
+    # host-memory arrays (chunked pipeline: several launches in flight on different streams)
+    u = fibonacci_sphere(700001)
+    np.testing.assert_array_equal(pers.evaluate_xyz(u, EARTH_20220114), plain.evaluate_xyz(u, EARTH_20220114))
+
+
 def test_multiband_rejects_unsupported():
     with pytest.raises(engine._cabi.ZodiError):
         zp.MultiBandModel([zp.Quantity(25.0, "um"), zp.Quantity(60.0, "um")], name="rrm-experimental").device_model

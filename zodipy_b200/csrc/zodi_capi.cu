@@ -131,6 +131,7 @@ struct DeviceGuard {
 };
 
 constexpr int kSlots = 3;  // pipeline depth of the host-memory path
+constexpr int kTileSlots = 64;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -168,6 +169,11 @@ struct zodi_model_s {
     Pair<float>* d_table32 = nullptr;
     Pair<float>* d_nodes32 = nullptr;
     unsigned long long* d_scratch = nullptr;  // 8 bytes for the max-radius reduction
+    // persistent-tile counters of the packed kernel (LaunchArgs::tile_counter): kTileSlots pairs handed out
+    // round robin, so launches of one model that overlap on different streams do not share a pair
+    unsigned int* d_tiles = nullptr;
+    std::atomic<unsigned> tile_slot{0};
+    int persist = 1;          // ZODI_X2_PERSIST: 0 never, 1 launches that store to peers (default), 2 always
     // host-memory path workspace
     std::mutex ws_mutex;
     Slot slots[kSlots];
@@ -233,6 +239,8 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     m->force_generic = (fg && fg[0] == '1');
     const char* nx = std::getenv("ZODI_NO_X2");
     m->no_x2 = (nx && nx[0] == '1');
+    const char* ps = std::getenv("ZODI_X2_PERSIST");
+    if (ps && ps[0] >= '0' && ps[0] <= '2') m->persist = ps[0] - '0';
 
     // ---- table as (B_i, B_{i+1}-B_i) pairs, nodes as (x_k, w_k) pairs ----
     std::vector<Pair<double>> t64, n64;
@@ -249,6 +257,10 @@ int upload_model(zodi_model_s* m, const zodi_model_desc* d) {
     CU_CHECK(put((void**)&m->d_table32, t32.data(), t32.size() * sizeof(Pair<float>)));
     CU_CHECK(put((void**)&m->d_nodes32, n32.data(), n32.size() * sizeof(Pair<float>)));
     if (!m->d_scratch) CU_CHECK(cudaMalloc((void**)&m->d_scratch, sizeof(unsigned long long)));
+    if (!m->d_tiles) {
+        CU_CHECK(cudaMalloc((void**)&m->d_tiles, kTileSlots * 2 * sizeof(unsigned int)));
+        CU_CHECK(cudaMemset(m->d_tiles, 0, kTileSlots * 2 * sizeof(unsigned int)));
+    }
 
     m->desc = *d;
     m->desc.temps = m->desc.bnu = m->desc.nodes = m->desc.weights = nullptr;
@@ -289,17 +301,34 @@ bool rrm_takes_packed(const zodi_model_s* m, int64_t n) {
     return m->rrm_x2_ok && !m->no_x2 && n >= (int64_t)sm_count() * 1024;
 }
 
+// Packed multi-band kernel (one thread per PAIR of lines of sight): once the pairs give every SM a CTA;
+// smaller inputs keep one line of sight per thread.
+bool multiband_takes_packed(const zodi_model_s* m, int64_t n) {
+    return !m->no_x2 && n >= (int64_t)sm_count() * 2 * kPackedDefaultThreads;
+}
+
 cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cudaStream_t stream) {
     if (a.n <= 0) return cudaSuccess;
     if (m->mb_bands > 0) {
-        if (precision == ZODI_FP32) return launch_multiband_f32(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+        if (precision == ZODI_FP32) {
+            if (multiband_takes_packed(m, a.shape_n > 0 ? a.shape_n : a.n))
+                return launch_multiband_packed(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+            return launch_multiband_f32(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+        }
         return launch_multiband_f64(m->mb64, a, m->d_mbtab64, m->d_nodes64, stream);
     }
     if (m->kelsall_ok && !m->force_generic) {
         // packed-fp32 kernels: every fp32 evaluation of a Kelsall-family model
-        if (precision == ZODI_FP32 && !m->no_x2)
-            return launch_kelsall_packed(m->k32, a, m->d_table32, m->d_nodes32,
-                                         pick_packed_shape(a.shape_n > 0 ? a.shape_n : a.n, m->k32.n_nodes, m->k32.n_comps), stream);
+        if (precision == ZODI_FP32 && !m->no_x2) {
+            const PackedShape shape = pick_packed_shape(a.shape_n > 0 ? a.shape_n : a.n, m->k32.n_nodes, m->k32.n_comps);
+            if (m->persist == 2 || (m->persist == 1 && a.n_peers > 0)) {
+                // persistent tiles (the launcher drops the counter again when the grid fits the machine anyway)
+                LaunchArgs b = a;
+                b.tile_counter = m->d_tiles + 2 * (m->tile_slot.fetch_add(1) % kTileSlots);
+                return launch_kelsall_packed(m->k32, b, m->d_table32, m->d_nodes32, shape, stream);
+            }
+            return launch_kelsall_packed(m->k32, a, m->d_table32, m->d_nodes32, shape, stream);
+        }
         if (precision == ZODI_FP32) return launch_kelsall_f32(m->k32, a, m->d_table32, m->d_nodes32, stream);
         return launch_kelsall_f64(m->k64, a, m->d_table64, m->d_nodes64, stream);
     }
@@ -610,6 +639,7 @@ int zodi_model_destroy(zodi_model_t m) {
         cudaFree(m->d_table64); cudaFree(m->d_nodes64);
         cudaFree(m->d_table32); cudaFree(m->d_nodes32);
         cudaFree(m->d_scratch);
+        cudaFree(m->d_tiles);
         cudaFree(m->d_mbtab64); cudaFree(m->d_mbtab32);
     }
     delete m;
@@ -991,35 +1021,12 @@ int zodi_multiband_create(const zodi_model_desc* descs, int32_t n_bands, int dev
         return fail(ZODI_ERR_UNSUPPORTED, "multi-band evaluation needs a Kelsall-family model layout");
     }
     DeviceGuard guard(device);
-    MultiBandModel<double>& MB = m->mb64;
-    std::memset(&MB, 0, sizeof(MB));
-    MB.base = m->k64;
-    MB.n_bands = n_bands;
-    MB.n_bands_padded = n_bands <= 4 ? 4 : (n_bands <= 8 ? 8 : 16);
-    const int nt = descs[0].n_temps;
-    std::vector<Pair<double>> t64((size_t)n_bands * nt);
-    std::vector<Pair<float>> t32((size_t)n_bands * nt);
-    for (int b = 0; b < n_bands; ++b) {
-        KelsallModel<double> kb;
-        if (!build_kelsall_model(descs[b], kb)) {
-            zodi_model_destroy(m);
-            return fail(ZODI_ERR_UNSUPPORTED, "band %d is not eligible for the fused kernel", b);
-        }
-        for (int c = 0; c < 6; ++c) { MB.aB[b][c] = kb.aB[c]; MB.aS[b][c] = kb.aS[c]; }
-        MB.C1p[b] = kb.C1p; MB.C2p[b] = kb.C2p; MB.C3l[b] = kb.C3l;
-        if (kb.scatter) MB.base.scatter = 1;
-        std::vector<Pair<double>> tb, nb;
-        std::vector<Pair<float>> tbf, nbf;
-        build_pairs(descs[b], tb, nb, tbf, nbf);
-        for (int i = 0; i < nt; ++i) { t64[(size_t)b * nt + i] = tb[i]; t32[(size_t)b * nt + i] = tbf[i]; }
-    }
-    MultiBandModel<float>& MF = m->mb32;
-    std::memset(&MF, 0, sizeof(MF));
-    narrow_kelsall(MB.base, MF.base);
-    MF.n_bands = MB.n_bands; MF.n_bands_padded = MB.n_bands_padded;
-    for (int b = 0; b < kMaxBands; ++b) {
-        for (int c = 0; c < 6; ++c) { MF.aB[b][c] = (float)MB.aB[b][c]; MF.aS[b][c] = (float)MB.aS[b][c]; }
-        MF.C1p[b] = (float)MB.C1p[b]; MF.C2p[b] = (float)MB.C2p[b]; MF.C3l[b] = (float)MB.C3l[b];
+    std::vector<Pair<double>> t64;
+    std::vector<Pair<float>> t32;
+    const int bad = build_multiband_model(descs, n_bands, m->mb64, m->mb32, t64, t32);
+    if (bad >= 0) {
+        zodi_model_destroy(m);
+        return fail(ZODI_ERR_UNSUPPORTED, "band %d is not eligible for the fused kernel", bad);
     }
     cudaError_t e = cudaMalloc((void**)&m->d_mbtab64, t64.size() * sizeof(Pair<double>));
     if (e == cudaSuccess) e = cudaMemcpy(m->d_mbtab64, t64.data(), t64.size() * sizeof(Pair<double>), cudaMemcpyHostToDevice);
@@ -1163,6 +1170,9 @@ int zodi_peer_rendezvous(int device, void* const* peer_flags, int32_t n_peers, i
 
 const char* zodi_model_kernel_for(zodi_model_t m, int64_t n, int32_t precision) {
     if (!m) return "";
+    if (m->mb_bands > 0)
+        return (precision == ZODI_FP32 && multiband_takes_packed(m, n)) ? "zodi_los_multiband_x2_kernel"
+                                                                         : "zodi_los_multiband_kernel";
     if (m->rrm_ok && !m->force_generic)
         return (precision == ZODI_FP32 && rrm_takes_packed(m, n)) ? "zodi_los_rrm_x2_kernel" : "zodi_los_rrm_kernel";
     if (!(m->kelsall_ok && !m->force_generic)) return "zodi_los_generic_kernel";

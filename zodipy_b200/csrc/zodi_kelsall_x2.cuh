@@ -25,9 +25,14 @@
 #define ZODI_X2_UNROLL 1  // node-loop unroll factor of the packed cloud + bands loop (measured: see DESIGN.md)
 #endif
 
+#ifndef ZODI_X2_RF_UNROLL
+#define ZODI_X2_RF_UNROLL 1  // node-loop unroll factor of the packed ring and feature loops (A/B)
+#endif
+
 namespace zodi {
 
 constexpr int kX2Unroll = ZODI_X2_UNROLL;
+constexpr int kX2RfUnroll = ZODI_X2_RF_UNROLL;
 
 struct alignas(8) F2 { float x, y; };
 
@@ -374,6 +379,9 @@ ZODI_HD void kelsall_ring_x2(const KelsallModel<float>& K, const Pair<float>* ta
     const F2 ox = f2(Pa.ox, Pb.ox), oy = f2(Pa.oy, Pb.oy), oz = f2(Pa.oz, Pb.oz);
     F2 acc = f2(0.f), accS = f2(0.f);
     const TableRef tref = table_ref(tab);
+#if defined(__CUDA_ARCH__)
+#pragma unroll kX2RfUnroll
+#endif
     for (int k = sub; k < K.n_nodes; k += L) {
         const Pair<float> nw = nodes[k];
         const F2 R_los = fma2(h, nw.a, mid);
@@ -421,6 +429,9 @@ ZODI_HD void kelsall_feature_x2(const KelsallModel<float>& K, const Pair<float>*
     const F2 cr = f2(Pa.cr, Pb.cr), sr = f2(Pa.sr, Pb.sr), msr = f2(-Pa.sr, -Pb.sr);
     F2 acc = f2(0.f), accS = f2(0.f);
     const TableRef tref = table_ref(tab);
+#if defined(__CUDA_ARCH__)
+#pragma unroll kX2RfUnroll
+#endif
     for (int k = sub; k < K.n_nodes; k += L) {
         const Pair<float> nw = nodes[k];
         const F2 R_los = fma2(h, nw.a, mid);

@@ -14,6 +14,7 @@
 #include "zodi_kelsall.cuh"
 #include "zodi_kelsall_x2.cuh"
 #include "zodi_multiband.cuh"
+#include "zodi_multiband_x2.cuh"
 #include "zodi_rrm.cuh"
 #include "zodi_rrm_x2.cuh"
 
@@ -56,6 +57,10 @@ struct LaunchArgs {
     const double* eph_obs_coef;  // same for the observer, or NULL: observer = eph_scale * Earth
     const double* obstime;
     int64_t eph_nseg;     double eph_t0, eph_dt, eph_scale;
+    // persistent tiles (packed Kelsall kernel): two zero-initialised counters {claimed, CTAs done}; the CTAs of
+    // a grid sized to the machine take further tiles from `claimed`, the last CTA to leave zeroes both again.
+    // NULL: one tile per CTA.
+    unsigned int* tile_counter = nullptr;
 };
 
 // Spline position at time t: interval i = floor((t - t0)/dt) clamped to the spline (scipy's PPoly
@@ -259,7 +264,7 @@ __device__ __forceinline__ void exchange_pre(const LosPre& mine, int sub, LosPre
     }
 }
 
-template <bool HAS_RF, bool SHARE13, bool SCATTER, int L, int THREADS, int MIN_CTAS>
+template <bool HAS_RF, bool SHARE13, bool SCATTER, int L, int THREADS, int MIN_CTAS, bool PERSIST = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
                            const __grid_constant__ LaunchArgs args,
@@ -273,7 +278,15 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
 
     constexpr int kGroups = THREADS / L;  // pair groups per CTA
     const int sub = threadIdx.x % L;
-    const int64_t j0 = (int64_t)blockIdx.x * (2 * kGroups) + threadIdx.x / L, j1 = j0 + kGroups;
+    // A tile = the 2 * kGroups lines of sight one CTA pass covers.  Default: tile = CTA.  PERSIST (tile counter
+    // given): the grid only fills the machine and every CTA claims further tiles as it finishes one: a CTA's slot is
+    // not released until its stores have been acknowledged, which for peer (NVLink) stores costs 1-2 us per
+    // CTA - 3-4 % of a 45 us tile at 8 GPUs; a persistent CTA pays that once, and its remote stores of one
+    // tile drain behind the next tile's arithmetic.
+    __shared__ unsigned int s_claim;
+    const unsigned int n_tiles = (unsigned int)((args.n + 2 * kGroups - 1) / (2 * kGroups));
+    for (unsigned int tile = blockIdx.x;;) {
+    const int64_t j0 = (int64_t)tile * (2 * kGroups) + threadIdx.x / L, j1 = j0 + kGroups;
     const bool act0 = j0 < args.n, act1 = j1 < args.n;
     const int64_t jj0 = act0 ? j0 : args.n - 1, jj1 = act1 ? j1 : args.n - 1;
 
@@ -326,6 +339,20 @@ zodi_los_kelsall_x2_kernel(const __grid_constant__ KelsallModel<float> model,
     if (!args.return_comps && sub == 0) {
         if (act0) store_out<float>(args, 0, j0, tot0);
         if (act1) store_out<float>(args, 0, j1, tot1);
+    }
+    if (!PERSIST) break;
+    __syncthreads();  // every thread has read the previous claim
+    if (threadIdx.x == 0) s_claim = atomicAdd(args.tile_counter, 1u);
+    __syncthreads();
+    tile = s_claim + gridDim.x;
+    if (tile >= n_tiles) break;
+    }
+    if (PERSIST && threadIdx.x == 0) {
+        // all claims of this CTA precede its `done` increment, so the CTA that completes the count may reset
+        if (atomicAdd(args.tile_counter + 1, 1u) == gridDim.x - 1) {
+            args.tile_counter[0] = 0u;
+            args.tile_counter[1] = 0u;
+        }
     }
 }
 
@@ -439,6 +466,45 @@ zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
         [&](int b, Real v) {
             if (active && b < model.n_bands) store_out<Real>(args, b, j, v);
         });
+}
+
+// Packed-fp32 multi-band kernel (zodi_multiband_x2.cuh): two lines of sight per thread (lines t and
+// t + THREADS of the CTA's block), tables staged knot-major.
+template <int NB, bool HAS_RF, bool SCATTER>
+__global__ void __launch_bounds__(kPackedDefaultThreads, 4)
+zodi_los_multiband_x2_kernel(const __grid_constant__ MultiBandModel<float> model,
+                             const __grid_constant__ LaunchArgs args,
+                             const Pair<float>* __restrict__ g_tables,   // [n_bands][n_temps]
+                             const Pair<float>* __restrict__ g_nodes) {
+    constexpr int kRow = MbRows<NB>::kRow;
+    __shared__ __align__(16) Pair<float> s_rows[kMultiBandMaxTemps * kRow];
+    __shared__ Pair<float> s_nodes[kFastMaxNodes];
+    const int nt = model.base.n_temps;
+    for (int i = threadIdx.x; i < nt * kRow; i += blockDim.x) {
+        const int knot = i / kRow, b = i - knot * kRow;
+        const Pair<float> zero = {0.f, 0.f};
+        s_rows[i] = (b < model.n_bands) ? g_tables[b * nt + knot] : zero;
+    }
+    for (int i = threadIdx.x; i < model.base.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
+    __syncthreads();
+
+    constexpr int T = kPackedDefaultThreads;
+    const int64_t j0 = (int64_t)blockIdx.x * (2 * T) + threadIdx.x, j1 = j0 + T;
+    const bool act0 = j0 < args.n, act1 = j1 < args.n;
+    const int64_t jj0 = act0 ? j0 : args.n - 1, jj1 = act1 ? j1 : args.n - 1;
+    auto prologue = [&](int64_t jj) {
+        double ux, uy, uz, ox, oy, oz, ex, ey;
+        load_direction(args, jj, ux, uy, uz);
+        load_positions(args, jj, HAS_RF, ox, oy, oz, ex, ey);
+        return los_pre<HAS_RF>(model.base, ux, uy, uz, ox, oy, oz, ex, ey, args.outside_mask);
+    };
+    const LosPre P0 = prologue(jj0), P1 = prologue(jj1);
+    integrate_multiband_x2<NB, HAS_RF, SCATTER>(model, s_rows, s_nodes, P0, P1, [&](int b, float va, float vb) {
+        if (b < model.n_bands) {
+            if (act0) store_out<float>(args, b, j0, va);
+            if (act1) store_out<float>(args, b, j1, vb);
+        }
+    });
 }
 
 }  // namespace zodi

@@ -40,6 +40,9 @@ cudaError_t launch_kelsall_packed(const KelsallModel<float>& K, const LaunchArgs
                                   const Pair<float>* nodes, PackedShape shape, cudaStream_t stream);
 cudaError_t launch_multiband_f32(const MultiBandModel<float>& MB, const LaunchArgs& a, const Pair<float>* tabs,
                                  const Pair<float>* nodes, cudaStream_t stream);
+// packed fp32 multi-band kernel (zodi_multiband_x2.cuh): two lines of sight per thread
+cudaError_t launch_multiband_packed(const MultiBandModel<float>& MB, const LaunchArgs& a, const Pair<float>* tabs,
+                                    const Pair<float>* nodes, cudaStream_t stream);
 cudaError_t launch_multiband_f64(const MultiBandModel<double>& MB, const LaunchArgs& a, const Pair<double>* tabs,
                                  const Pair<double>* nodes, cudaStream_t stream);
 // fused RRM kernels (zodi_rrm.cuh)

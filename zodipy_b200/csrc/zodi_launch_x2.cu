@@ -28,8 +28,19 @@ cudaError_t launch_T(const KelsallModel<float>& K, const LaunchArgs& a, const Pa
     const int64_t grid = (a.n + per_cta - 1) / per_cta;
     constexpr int kCtas256 = SCATTER ? 3 : (HAS_RF ? ZODI_X2_CTAS_RF : ZODI_X2_CTAS_THERMAL);
     constexpr int kMinCtas = kCtas256 * (256 / THREADS);
-    zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, L, THREADS, kMinCtas>
-        <<<(unsigned)grid, THREADS, 0, stream>>>(K, a, tab, nodes);
+    // persistent tiles (LaunchArgs::tile_counter; instantiated for the large-N shape only: L = 1, 128-thread
+    // CTAs): one resident wave of CTAs, each claiming tiles until none is left
+    bool persistent = false;
+    if constexpr (L == 1 && THREADS == 128) {
+        if (a.tile_counter != nullptr && grid > (int64_t)sm_count() * kMinCtas) {
+            zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, 1, 128, kMinCtas, true>
+                <<<(unsigned)(sm_count() * kMinCtas), 128, 0, stream>>>(K, a, tab, nodes);
+            persistent = true;
+        }
+    }
+    if (!persistent)
+        zodi_los_kelsall_x2_kernel<HAS_RF, SHARE13, SCATTER, L, THREADS, kMinCtas>
+            <<<(unsigned)grid, THREADS, 0, stream>>>(K, a, tab, nodes);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -11,6 +11,7 @@
 #include "zodi_kelsall.cuh"
 #include "zodi_rrm.cuh"
 #include "zodi_rrm_x2.cuh"
+#include "zodi_multiband.cuh"
 
 namespace zodi {
 
@@ -278,6 +279,41 @@ inline void narrow_kelsall(const KelsallModel<From>& a, KelsallModel<To>& b) {
     b.cutA_in = a.cutA_in; b.cutA_out = a.cutA_out; b.cutR_in = a.cutR_in; b.cutR_out = a.cutR_out;
     b.cutF_in = a.cutF_in; b.cutF_out = a.cutF_out;
     b.f_cos0 = a.f_cos0; b.f_sin0 = a.f_sin0;
+}
+
+// Multi-band form (zodi_multiband.cuh) of n_bands descriptors that differ only in their spectral parameters:
+// band 0's geometry plus the per-band source-function scalars and one blackbody table per band
+// ([band][knot]).  Returns the index of the first band that is not eligible for the fused layout, -1 if all are.
+inline int build_multiband_model(const zodi_model_desc* descs, int n_bands, MultiBandModel<double>& MB,
+                                 MultiBandModel<float>& MF, std::vector<Pair<double>>& t64,
+                                 std::vector<Pair<float>>& t32) {
+    std::memset(&MB, 0, sizeof(MB));
+    std::memset(&MF, 0, sizeof(MF));
+    if (!build_kelsall_model(descs[0], MB.base)) return 0;
+    MB.base.scatter = 0;
+    MB.n_bands = n_bands;
+    MB.n_bands_padded = n_bands <= 4 ? 4 : (n_bands <= 8 ? 8 : 16);
+    const int nt = descs[0].n_temps;
+    t64.assign((size_t)n_bands * nt, Pair<double>{0.0, 0.0});
+    t32.assign((size_t)n_bands * nt, Pair<float>{0.f, 0.f});
+    for (int b = 0; b < n_bands; ++b) {
+        KelsallModel<double> kb;
+        if (!build_kelsall_model(descs[b], kb)) return b;
+        for (int c = 0; c < 6; ++c) { MB.aB[b][c] = kb.aB[c]; MB.aS[b][c] = kb.aS[c]; }
+        MB.C1p[b] = kb.C1p; MB.C2p[b] = kb.C2p; MB.C3l[b] = kb.C3l;
+        if (kb.scatter) { MB.base.scatter = 1; MB.scatter_bands |= 1u << b; }
+        std::vector<Pair<double>> tb, nb;
+        std::vector<Pair<float>> tbf, nbf;
+        build_pairs(descs[b], tb, nb, tbf, nbf);
+        for (int i = 0; i < nt; ++i) { t64[(size_t)b * nt + i] = tb[i]; t32[(size_t)b * nt + i] = tbf[i]; }
+    }
+    narrow_kelsall(MB.base, MF.base);
+    MF.n_bands = MB.n_bands; MF.n_bands_padded = MB.n_bands_padded; MF.scatter_bands = MB.scatter_bands;
+    for (int b = 0; b < kMaxBands; ++b) {
+        for (int c = 0; c < 6; ++c) { MF.aB[b][c] = (float)MB.aB[b][c]; MF.aS[b][c] = (float)MB.aS[b][c]; }
+        MF.C1p[b] = (float)MB.C1p[b]; MF.C2p[b] = (float)MB.C2p[b]; MF.C3l[b] = (float)MB.C3l[b];
+    }
+    return -1;
 }
 
 // RRM fast path: returns false unless the model has the shipped rrm-experimental layout (zodi_rrm.cuh):

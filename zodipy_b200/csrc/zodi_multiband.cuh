@@ -28,6 +28,7 @@ struct MultiBandModel {
     Real aB[kMaxBands][6];    // (1 - albedo) * emissivity * amplitude   per band and component
     Real aS[kMaxBands][6];    // albedo * F_sun * N_phase * amplitude
     Real C1p[kMaxBands], C2p[kMaxBands], C3l[kMaxBands];  // phase function per band (C3 * log2e)
+    uint32_t scatter_bands;   // bit b: band b has a non-zero albedo (packed kernel: scattering term per band)
 };
 
 // Table coordinate -> (segment index, fraction): table_coord() of zodi_device.cuh.
