@@ -451,7 +451,7 @@ void set_ephemeris(LaunchArgs& la, const zodi_ephemeris_s* e, const double* obst
 }
 
 void set_healpix(LaunchArgs& la, const zodi_healpix_args* hp, int64_t offset) {
-    la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0;
+    la.cyc_block = 0; la.cyc_parts = 1; la.cyc_rank = 0; la.cyc_shift = -1;
     set_ephemeris(la, nullptr, nullptr);
     la.hp_nside = 0; la.hp_start = 0; la.hp_rotate = 0; la.hp_nest = 0;
     la.lon = nullptr; la.lat = nullptr;
@@ -708,6 +708,9 @@ static int evaluate_impl(zodi_model_t m, const zodi_eval_args* a, const zodi_hea
     if (ll) set_lonlat(la, ll, ll->lon, ll->lat);
     if (a->ephemeris) set_ephemeris(la, a->ephemeris, a->obstime);
     la.cyc_block = a->cyclic_block; la.cyc_parts = a->cyclic_parts; la.cyc_rank = a->cyclic_rank;
+    la.cyc_shift = -1;
+    if (la.cyc_block > 0 && (la.cyc_block & (la.cyc_block - 1)) == 0)
+        for (int sh = 0; sh < 62; ++sh) if ((int64_t(1) << sh) == la.cyc_block) la.cyc_shift = sh;
     CU_CHECK(launch_eval(m, la, a->precision, (cudaStream_t)a->stream));
     return ZODI_OK;
 }

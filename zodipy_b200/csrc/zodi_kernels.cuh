@@ -52,6 +52,7 @@ struct LaunchArgs {
     const double* lon;    const double* lat;
     // block-cyclic shard layout (see zodi_eval_args.cyclic_block); 0 = identity
     int64_t cyc_block;    int cyc_parts;      int cyc_rank;
+    int cyc_shift = -1;   // log2(cyc_block) when it is a power of two (shift / mask instead of a 64-bit division)
     // on-device ephemeris (time-ordered data): positions from cubic splines at obstime[j]
     const double* eph_coef;   // [n_knots-1][3][4] Earth (highest power first); NULL = use obs/earth arrays
     const double* eph_obs_coef;  // same for the observer, or NULL: observer = eph_scale * Earth
@@ -100,6 +101,10 @@ __device__ __forceinline__ void load_positions(const LaunchArgs& a, int64_t jj, 
 // Global index of local line of sight j under the (optional) block-cyclic layout.
 __device__ __forceinline__ int64_t global_index(const LaunchArgs& a, int64_t j) {
     if (a.cyc_block <= 0) return j;
+    if (a.cyc_shift >= 0) {
+        const int64_t lb = j >> a.cyc_shift;
+        return (((lb * a.cyc_parts + a.cyc_rank)) << a.cyc_shift) + (j & (a.cyc_block - 1));
+    }
     const int64_t lb = j / a.cyc_block;
     return (lb * a.cyc_parts + a.cyc_rank) * a.cyc_block + (j - lb * a.cyc_block);
 }
