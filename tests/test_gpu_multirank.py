@@ -202,7 +202,7 @@ def _worker_persistent(rank, world, port, backend, nside, name, x, unit, queue):
     import zodipy_b200 as zp
     from zodipy_b200 import sharding
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ZODI_X2_PERSIST="1")  # opt-in knob
     dev_index = rank if backend == "nccl" else 0
     torch.cuda.set_device(dev_index)
     dev = torch.device("cuda", dev_index)

@@ -173,7 +173,10 @@ struct zodi_model_s {
     // round robin, so launches of one model that overlap on different streams do not share a pair
     unsigned int* d_tiles = nullptr;
     std::atomic<unsigned> tile_slot{0};
-    int persist = 1;          // ZODI_X2_PERSIST: 0 never, 1 launches that store to peers (default), 2 always
+    // ZODI_X2_PERSIST: 0 one tile per CTA (default), 1 persistent tiles for launches that store to peers,
+    // 2 for every large launch.  Opt-in: measured -0.5 % at 2 GPUs in one pass and +2 ... +3.6 % at 2 - 8 GPUs
+    // in another, so the plain grid stays the default.
+    int persist = 0;
     // host-memory path workspace
     std::mutex ws_mutex;
     Slot slots[kSlots];
