@@ -15,6 +15,8 @@ for w in $WHAT; do
     dirbe64) name=${TAG}_x2_dirbe_nside64; args="--name dirbe --x 25 --unit um --nside 64";;
     fp64) name=${TAG}_fp64_planck18_nside1024; args="--name planck18 --x 857 --unit GHz --nside 1024 --precision fp64";;
     rrm) name=${TAG}_rrm_nside512; args="--name rrm-experimental --x 25 --unit um --nside 512";;
+    mb) name=${TAG}_multiband_x2_dirbe10_nside512; args="--name dirbe --unit um --nside 512 --bands 1.25,2.2,3.5,4.9,12,25,60,100,140,240";;
+    mbp) name=${TAG}_multiband_x2_planck6_nside1024; args="--name planck18 --unit GHz --nside 1024 --bands 100,143,217,353,545,857";;
     rrm64) name=${TAG}_rrm_fp64_nside256; args="--name rrm-experimental --x 25 --unit um --nside 256 --precision fp64";;
   esac
   $NCU -o gpurun_out/$name $T $args > gpurun_out/ncu_$w.log 2>&1

@@ -30,7 +30,18 @@ def main() -> None:
     ap.add_argument("--arrays", action="store_true",
                     help="device-resident (3, N) unit vectors as input (bench.py's `value` path) instead of "
                          "directions generated in the kernel prologue")
+    ap.add_argument("--bands", default="", help="comma-separated wavelengths / frequencies: MultiBandModel of "
+                                                "these bands instead of the single band --x")
     args = ap.parse_args()
+    if args.bands:
+        mb = zp.MultiBandModel([zp.Quantity(float(b), args.unit) for b in args.bands.split(",")], name=args.name,
+                               precision=args.precision)
+        for _ in range(args.launches):
+            mb.evaluate_healpix(args.nside, EARTH, device_out=True,
+                                out_dtype=np.float32 if args.precision == "fp32" else np.float64)
+        torch.cuda.synchronize()
+        print(mb.device_model.kernel_name_for(12 * args.nside**2, args.precision))
+        return
     model = zp.Model(zp.Quantity(args.x, args.unit), name=args.name, precision=args.precision)
     dtype = np.float32 if args.precision == "fp32" else np.float64
     if args.arrays:

@@ -474,9 +474,17 @@ zodi_los_multiband_kernel(const __grid_constant__ MultiBandModel<Real> model,
 }
 
 // Packed-fp32 multi-band kernel (zodi_multiband_x2.cuh): two lines of sight per thread (lines t and
-// t + THREADS of the CTA's block), tables staged knot-major.
+// t + THREADS of the CTA's block), tables staged knot-major.  Resident 128-thread CTAs per SM: 8 (64
+// registers) up to 8 bands, 6 (80 registers) for 16 - the node loop is a long dependent chain, so warps in
+// flight count for more than the handful of spilled prologue values (4 CTAs: 74 - 110 registers, no spills).
+#ifndef ZODI_MBX2_CTAS
+#define ZODI_MBX2_CTAS 8
+#endif
+#ifndef ZODI_MBX2_CTAS_16
+#define ZODI_MBX2_CTAS_16 6
+#endif
 template <int NB, bool HAS_RF, bool SCATTER>
-__global__ void __launch_bounds__(kPackedDefaultThreads, 4)
+__global__ void __launch_bounds__(kPackedDefaultThreads, (NB <= 8 ? ZODI_MBX2_CTAS : ZODI_MBX2_CTAS_16))
 zodi_los_multiband_x2_kernel(const __grid_constant__ MultiBandModel<float> model,
                              const __grid_constant__ LaunchArgs args,
                              const Pair<float>* __restrict__ g_tables,   // [n_bands][n_temps]
