@@ -33,3 +33,13 @@ $S $RRM \
 for f in x2_planck18_nside2048_arrays fp64_planck18_nside2048_arrays x2_dirbe_nside1024; do
   python tools/ncu_source_hot.py gpurun_out/r2k_$f.source.csv --top 12 > profiles/r2_ncu_${f}_source_hot.txt
 done
+# packed multi-band kernel (pass Q capture)
+if [ -f gpurun_out/r2q_multiband_x2_planck6_nside1024.raw.csv ]; then
+  $S gpurun_out/r2q_multiband_x2_planck6_nside1024.raw.csv \
+    --title "ncu --set full, zodi_los_multiband_x2_kernel<NB=8, cloud+bands>, planck18 6 channels nside 1024 fp32, round-2 final build" \
+    --command "$CMD --name planck18 --unit GHz --nside 1024 --bands 100,143,217,353,545,857" \
+    --workload "12 582 912 lines of sight x 6 bands x 4 comps x 50 nodes = 1.5099e10 band-evaluations in one launch, pixel directions generated in the kernel prologue" \
+    --los 12582912 --evals 1.50994944e10 $C --counts-key planck18_multiband6_fp32_packed --source profiles/r2_ncu_multiband_x2_planck6_nside1024.md \
+    > profiles/r2_ncu_multiband_x2_planck6_nside1024.md
+  python tools/ncu_source_hot.py gpurun_out/r2q_multiband_x2_planck6_nside1024.source.csv --top 12 > profiles/r2_ncu_multiband_x2_planck6_nside1024_source_hot.txt
+fi

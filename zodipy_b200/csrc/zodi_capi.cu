@@ -162,6 +162,7 @@ struct zodi_model_s {
     MultiBandModel<float> mb32;
     Pair<double>* d_mbtab64 = nullptr;  // [n_bands][n_temps]
     Pair<float>* d_mbtab32 = nullptr;
+    Pair<float>* d_mbrows32 = nullptr;  // the same tables knot-major, n_bands_padded + 2 pairs per row (packed kernel)
     int force_generic = 0;    // testing knob (ZODI_FORCE_GENERIC=1): always use the generic kernel
     int no_x2 = 0;            // testing knob (ZODI_NO_X2=1): scalar fused kernel instead of packed
     Pair<double>* d_table64 = nullptr;
@@ -315,7 +316,7 @@ cudaError_t launch_eval(zodi_model_s* m, const LaunchArgs& a, int precision, cud
     if (m->mb_bands > 0) {
         if (precision == ZODI_FP32) {
             if (multiband_takes_packed(m, a.shape_n > 0 ? a.shape_n : a.n))
-                return launch_multiband_packed(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
+                return launch_multiband_packed(m->mb32, a, m->d_mbrows32, m->d_nodes32, stream);
             return launch_multiband_f32(m->mb32, a, m->d_mbtab32, m->d_nodes32, stream);
         }
         return launch_multiband_f64(m->mb64, a, m->d_mbtab64, m->d_nodes64, stream);
@@ -643,7 +644,7 @@ int zodi_model_destroy(zodi_model_t m) {
         cudaFree(m->d_table32); cudaFree(m->d_nodes32);
         cudaFree(m->d_scratch);
         cudaFree(m->d_tiles);
-        cudaFree(m->d_mbtab64); cudaFree(m->d_mbtab32);
+        cudaFree(m->d_mbtab64); cudaFree(m->d_mbtab32); cudaFree(m->d_mbrows32);
     }
     delete m;
     return ZODI_OK;
@@ -1038,6 +1039,13 @@ int zodi_multiband_create(const zodi_model_desc* descs, int32_t n_bands, int dev
     if (e == cudaSuccess) e = cudaMemcpy(m->d_mbtab64, t64.data(), t64.size() * sizeof(Pair<double>), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_mbtab32, t32.size() * sizeof(Pair<float>));
     if (e == cudaSuccess) e = cudaMemcpy(m->d_mbtab32, t32.data(), t32.size() * sizeof(Pair<float>), cudaMemcpyHostToDevice);
+    // knot-major copy for the packed kernel (MbRows<NB>::kRow pairs per row, bands past n_bands zero)
+    const int nt = descs[0].n_temps, row = m->mb32.n_bands_padded + 2;
+    std::vector<Pair<float>> rows((size_t)nt * row, Pair<float>{0.f, 0.f});
+    for (int knot = 0; knot < nt; ++knot)
+        for (int b = 0; b < n_bands; ++b) rows[(size_t)knot * row + b] = t32[(size_t)b * nt + knot];
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_mbrows32, rows.size() * sizeof(Pair<float>));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_mbrows32, rows.data(), rows.size() * sizeof(Pair<float>), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         zodi_model_destroy(m);
         return fail(ZODI_ERR_CUDA, "multi-band table upload failed: %s", cudaGetErrorString(e));

@@ -487,16 +487,16 @@ template <int NB, bool HAS_RF, bool SCATTER>
 __global__ void __launch_bounds__(kPackedDefaultThreads, (NB <= 8 ? ZODI_MBX2_CTAS : ZODI_MBX2_CTAS_16))
 zodi_los_multiband_x2_kernel(const __grid_constant__ MultiBandModel<float> model,
                              const __grid_constant__ LaunchArgs args,
-                             const Pair<float>* __restrict__ g_tables,   // [n_bands][n_temps]
+                             const Pair<float>* __restrict__ g_rows,     // [n_temps][NB + 2], knot-major
                              const Pair<float>* __restrict__ g_nodes) {
     constexpr int kRow = MbRows<NB>::kRow;
     __shared__ __align__(16) Pair<float> s_rows[kMultiBandMaxTemps * kRow];
     __shared__ Pair<float> s_nodes[kFastMaxNodes];
-    const int nt = model.base.n_temps;
-    for (int i = threadIdx.x; i < nt * kRow; i += blockDim.x) {
-        const int knot = i / kRow, b = i - knot * kRow;
-        const Pair<float> zero = {0.f, 0.f};
-        s_rows[i] = (b < model.n_bands) ? g_tables[b * nt + knot] : zero;
+    {   // rows are staged as they lie in HBM (the host transposed them): 16-byte copies, kRow is even
+        const float4* src = reinterpret_cast<const float4*>(g_rows);
+        float4* dst = reinterpret_cast<float4*>(s_rows);
+        const int n16 = model.base.n_temps * (kRow / 2);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     }
     for (int i = threadIdx.x; i < model.base.n_nodes; i += blockDim.x) s_nodes[i] = g_nodes[i];
     __syncthreads();
