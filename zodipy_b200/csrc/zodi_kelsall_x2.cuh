@@ -26,7 +26,9 @@
 #endif
 
 #ifndef ZODI_X2_RF_UNROLL
-#define ZODI_X2_RF_UNROLL 1  // node-loop unroll factor of the packed ring and feature loops (A/B)
+// node-loop unroll factor of the packed ring and feature loops: 5 (with 64 registers, see zodi_launch_x2.cu)
+// measured 2 - 7 % faster than 1 over nside 32 ... 1024 (profiles/r2_ab_ring_feature_unroll_sweep.jsonl)
+#define ZODI_X2_RF_UNROLL 5
 #endif
 
 namespace zodi {

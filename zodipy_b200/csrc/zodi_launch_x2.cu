@@ -8,9 +8,10 @@ namespace {
 constexpr int L = ZODI_TU_LANES;
 
 // 5 CTAs of 256 threads per SM (48 registers): cloud+bands only measured 5 % faster than 4 CTAs/SM (60
-// registers) and 0.4 % faster than 6 (40 registers); with the ring/feature loops 5 CTAs/SM is 0.8 % faster
-// than 4 (64 registers) - the spills it causes sit in the per-line-of-sight prologue / epilogue, not in the
-// node loops.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  128-thread CTAs
+// registers) and 0.4 % faster than 6 (40 registers).  With the ring/feature loops: 4 CTAs/SM (64 registers)
+// and those two loops unrolled x5 - their per-node chains (sqrt / lg2 / ex2 / table / ex2) then overlap - is
+// 2.2 % (nside 1024) to 6.8 % (nside 64) faster than 5 CTAs/SM without unrolling; without unrolling the two
+// occupancies measured equal.  The scattering terms need more registers (3 CTAs/SM; 4 measured equal).  128-thread CTAs
 // keep the same number of resident warps in twice as many, half as long CTAs (shorter tail of a launch);
 // 64-thread CTAs measured the same again (profiles/r2_packed_cta_size_sweep.jsonl, r2_bench_n8_t128.json)
 // and were dropped.
@@ -18,7 +19,7 @@ constexpr int L = ZODI_TU_LANES;
 #define ZODI_X2_CTAS_THERMAL 5
 #endif
 #ifndef ZODI_X2_CTAS_RF
-#define ZODI_X2_CTAS_RF 5
+#define ZODI_X2_CTAS_RF 4  // 64 registers: room for the ring / feature loops unrolled x5 (ZODI_X2_RF_UNROLL)
 #endif
 
 template <bool HAS_RF, bool SHARE13, bool SCATTER, int THREADS>
