@@ -255,6 +255,8 @@ MULTIBAND_SETS = [
     ("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um"),  # scattering in 3 of 10 bands
     ("planck18", [100.0, 143.0, 217.0, 353.0, 545.0, 857.0], "GHz"),
     ("dirbe", [25.0, 60.0, 100.0], "um"),
+    ("planck13", [353.0, 545.0, 857.0], "GHz"),            # four components, other band geometry
+    ("odegard", [100.0, 143.0, 217.0, 300.0, 353.0, 450.0, 545.0, 700.0, 857.0], "GHz"),  # NB = 16, 9 bands
 ]
 
 
