@@ -13,7 +13,8 @@ EARTH = np.array([[-0.3919640703], [0.9020953332], [0.0]])
 rng = np.random.default_rng(0)
 u = rng.normal(size=(3, 40001))
 u /= np.linalg.norm(u, axis=0)
-for name, xs, unit in (("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um"),
+only_persistent = "--persistent-only" in sys.argv
+for name, xs, unit in () if only_persistent else (("dirbe", [1.25, 2.2, 3.5, 4.9, 12.0, 25.0, 60.0, 100.0, 140.0, 240.0], "um"),
                        ("planck18", [100.0, 143.0, 217.0, 353.0, 545.0, 857.0], "GHz"),
                        ("dirbe", [25.0, 60.0, 100.0], "um")):
     mb = zp.MultiBandModel([zp.Quantity(x, unit) for x in xs], name=name, precision="fp32")
